@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the warp / filter engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one ``warp_perspective`` call on a synthetic B x 3 x 1080 x 1920 fp32 batch
+(BASELINE.json configs[1]: bilinear, zeros padding, align_corners=True), B per GPU fixed (weak
+scaling: the batch dimension shards with no data-path collective).
+
+One JSON line on stdout (rank 0):
+  value     Mpix/s, whole job, inputs resident in HBM, through the public Python API
+            (prelude + kernel), CUDA events around exactly K steps, max over ranks
+  roofline  the fused warp kernel alone: CUDA events around each launch inside the timed region,
+            algorithmic bytes = 24 B/pixel (read 3 fp32 + write 3 fp32)
+  e2e       same metric with HOST buffers: pinned src -> H2D -> kernel -> D2H of the full output,
+            chunked and pipelined over three streams, copies inside the timed region
+  cpu_baseline  the oracle's torch-op port of the reference composition on the host cores,
+            bounded sample (rank 0, N=1 only)
+``--impl reference`` times that CPU port alone (the reference is pure Python and cannot travel to
+the GPU box; the port issues the same ATen calls: oracle/kornia_restated.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H_IMG, W_IMG, C_IMG = 1080, 1920, 3
+BYTES_PER_PIX = 24.0  # algorithmic: 3 channels x 4 B read + 3 x 4 B written per output pixel
+METRIC = "Mpix/s warp_perspective Bx3x1080x1920 fwd bilinear fp32"
+
+
+# ------------------------------------------------------------------------------------------ inputs
+def perspective_from_quads(src_q: torch.Tensor, dst_q: torch.Tensor) -> torch.Tensor:
+    """DLT: the (B,3,3) homography mapping 4 source corners to 4 destination corners (what
+    kornia.geometry.get_perspective_transform returns; used by the reference's flagship benchmark,
+    benchmarks/geometry/flagship.py:101-107).  Solved in float64 on the host."""
+    s, d = src_q.double(), dst_q.double()
+    B = s.shape[0]
+    A = torch.zeros(B, 8, 8, dtype=torch.float64)
+    b = torch.zeros(B, 8, dtype=torch.float64)
+    for i in range(4):
+        x, y, u, v = s[:, i, 0], s[:, i, 1], d[:, i, 0], d[:, i, 1]
+        A[:, 2 * i, 0], A[:, 2 * i, 1], A[:, 2 * i, 2] = x, y, 1.0
+        A[:, 2 * i, 6], A[:, 2 * i, 7] = -u * x, -u * y
+        A[:, 2 * i + 1, 3], A[:, 2 * i + 1, 4], A[:, 2 * i + 1, 5] = x, y, 1.0
+        A[:, 2 * i + 1, 6], A[:, 2 * i + 1, 7] = -v * x, -v * y
+        b[:, 2 * i], b[:, 2 * i + 1] = u, v
+    hvec = torch.linalg.solve(A, b)
+    return torch.cat([hvec, torch.ones(B, 1, dtype=torch.float64)], 1).view(B, 3, 3).float()
+
+
+def make_homographies(B: int, seed: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    quad = torch.tensor([[0.0, 0.0], [W_IMG - 1.0, 0.0], [W_IMG - 1.0, H_IMG - 1.0], [0.0, H_IMG - 1.0]]).expand(B, 4, 2)
+    return perspective_from_quads(quad, quad + 8.0 * torch.randn(B, 4, 2, generator=g))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU port
+def cpu_reference_run(steps: int, warmup: int, sample_b: int):
+    """Time the oracle's torch-op port of the reference on the host cores (all threads)."""
+    from oracle import kornia_restated as R
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    src = torch.rand(sample_b, C_IMG, H_IMG, W_IMG, generator=g)
+    M = make_homographies(sample_b, 0)
+    for _ in range(warmup):
+        R.warp_perspective(src, M, (H_IMG, W_IMG))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.warp_perspective(src, M, (H_IMG, W_IMG))
+    dt = (time.perf_counter() - t0) / steps
+    mpix = sample_b * H_IMG * W_IMG / dt / 1e6
+    return mpix, dt * 1e3, cores
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 8
+    mpix, ms, cores = cpu_reference_run(args.steps, max(args.warmup, 1), sample_b)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"warp_perspective fwd B={args.batch}x3x1080x1920 bilinear zeros align_corners=True",
+                   "per_step_sample": f"B={sample_b} of the batch (CPU per-image throughput is batch independent)"},
+        "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                         "sample": f"B={sample_b}x3x1080x1920 per step, torch CPU, {cores} threads"},
+        "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ ours
+def e2e_run(K, M_dev, B, steps, warmup, chunk, dev):
+    """Host-buffer throughput: pinned src -> device -> warp -> pinned dst, chunked over 3 streams."""
+    n_el = B * C_IMG * H_IMG * W_IMG
+    try:
+        src_h = torch.empty((B, C_IMG, H_IMG, W_IMG), dtype=torch.float32, pin_memory=True)
+        dst_h = torch.empty((B, C_IMG, H_IMG, W_IMG), dtype=torch.float32, pin_memory=True)
+    except RuntimeError as e:  # not enough lockable host memory
+        return None, f"pinned allocation failed: {e}"
+    # cheap deterministic fill (content does not affect timing)
+    src_h.view(-1)[: 1 << 20].uniform_()
+    src_h.view(-1)[1 << 20:] = 0.5
+    s_in, s_k, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    nbuf = 3
+    d_in = [torch.empty((chunk, C_IMG, H_IMG, W_IMG), device=dev) for _ in range(nbuf)]
+    d_out = [None] * nbuf
+    ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_k = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+
+    def one_step():
+        for i, b0 in enumerate(range(0, B, chunk)):
+            j = i % nbuf
+            n = min(chunk, B - b0)
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_k[j])  # the kernel that last read this input buffer is done
+                d_in[j][:n].copy_(src_h[b0:b0 + n], non_blocking=True)
+                ev_in[j].record(s_in)
+            with torch.cuda.stream(s_k):
+                s_k.wait_event(ev_in[j])
+                s_k.wait_event(ev_out[j])  # previous result in this slot has left the device
+                d_out[j] = K.warp_perspective(d_in[j][:n], M_dev[b0:b0 + n], (H_IMG, W_IMG))
+                ev_k[j].record(s_k)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_k[j])
+                dst_h[b0:b0 + n].copy_(d_out[j], non_blocking=True)
+                ev_out[j].record(s_out)
+        for s in (s_in, s_k, s_out):
+            torch.cuda.current_stream(dev).wait_stream(s)
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize(dev)
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        one_step()
+    t1.record()
+    torch.cuda.synchronize(dev)
+    ms = t0.elapsed_time(t1) / steps
+    del src_h, dst_h
+    return ms, f"pinned host buffers, chunk={chunk} samples, 3 streams (H2D / kernel / D2H), {n_el * 4} B each way per step"
+
+
+def run_ours(args) -> None:
+    import kornia_b200 as K
+    from kornia_b200 import _lib, _ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; kornia_b200 has no CPU path (use --impl reference for the CPU port)")
+    _lib.load()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    # per-rank shard generated in place: no scatter needed, seed = 1000 + rank
+    torch.manual_seed(1000 + rank)
+    src = torch.rand(B, C_IMG, H_IMG, W_IMG, device=dev)
+    M = make_homographies(B, 1000 + rank).to(dev)
+    dsize = (H_IMG, W_IMG)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        out = K.warp_perspective(src, M, dsize)
+    variant = _lib.last_warp_variant()
+    barrier()
+    _ops.kernel_events = []
+    launches0 = _ops.launch_count
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        t0.record()
+        for _ in range(args.steps):
+            out = K.warp_perspective(src, M, dsize)
+        t1.record()
+        barrier()
+    total_ms = t0.elapsed_time(t1)
+    kern_ms = [s.elapsed_time(e) for (_, s, e) in _ops.kernel_events]
+    _ops.kernel_events = None
+    launches = _ops.launch_count - launches0
+    checksum = float(out[0, :, ::97, ::89].sum())  # touch the result
+    del out
+    if dist is not None:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_step = total_ms / args.steps
+    pix_step = world * B * H_IMG * W_IMG
+    value = pix_step / (ms_step * 1e-3) / 1e6
+
+    # ---------------------------------------------------------------- e2e (host buffers)
+    e2e_ms, e2e_note = e2e_run(K, M, B, steps=max(2, min(args.steps, 3)), warmup=1, chunk=args.e2e_chunk, dev=dev)
+    if dist is not None and e2e_ms is not None:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = None, "fallback 6650 GB/s (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak = float(peaks["hbm_gbs"])
+        peak_src = "measured MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    except Exception:
+        peak = 6650.0
+    k_ms = statistics.mean(kern_ms) if kern_ms else float("nan")
+    achieved = BYTES_PER_PIX * B * H_IMG * W_IMG / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # per-launch DRAM bytes of the same kernel from the committed ncu capture, if any
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "warp_fwd_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        mpix, ms, cores = cpu_reference_run(steps=3, warmup=1, sample_b=8)
+        cpu = {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port",
+               "sample": f"3 steps of B=8x3x1080x1920 ({ms:.0f} ms each) with torch CPU ops, {cores} threads: oracle/kornia_restated.py"}
+
+    bytes_step = B * C_IMG * H_IMG * W_IMG * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"warp_perspective fwd B={B}x3x1080x1920 per GPU, bilinear, zeros, align_corners=True (BASELINE.json configs[1])",
+                   "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                   "l2": "inputs (6.37 GB/GPU) exceed the 126 MB L2; no explicit flush", "kernel_variant": variant,
+                   "homographies": "corner quad jittered by 8*randn px (benchmarks/geometry/flagship.py recipe), seed 1000+rank"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel_ms": k_ms, "kernel_launches_timed": len(kern_ms), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": BYTES_PER_PIX * B * H_IMG * W_IMG},
+        "cpu_baseline": cpu,
+        "e2e": ({"value": pix_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": bytes_step,
+                 "d2h_bytes_per_step": bytes_step, "ms_per_step": e2e_ms, "note": e2e_note}
+                if e2e_ms is not None else {"value": None, "unit": "Mpix/s", "note": e2e_note}),
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "checksum": checksum,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=256, help="samples per GPU")
+    ap.add_argument("--e2e-chunk", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,118 @@
+/*
+ * kornia_b200 -- C ABI of the B200-native warp / filter engine.
+ *
+ * The reference (kornia 0.9.0rc1) has no FFI: its boundary for this path is a set of Python
+ * functions that bottom out in ATen calls.  Each entry point below replaces one such ATen
+ * call site *together with* the elementwise Kornia code that feeds it, and is what a binding
+ * (ctypes / cffi / pybind / a TORCH_LIBRARY shim) would bind.  Paths are relative to the
+ * reference checkout.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense row-major NCHW (images), (B,3,3) (matrices), (B,h,w) (maps);
+ *   - `dtype` selects the element type of every floating buffer of the call (KB200_F32/F64);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - return value: 0 on success, a negative KB200_E* code otherwise; kb200_last_error()
+ *     returns a thread-local message for the last failing call;
+ *   - no entry point allocates device memory: scratch is caller-provided (see *_workspace_bytes).
+ */
+#ifndef KORNIA_B200_H
+#define KORNIA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB200_ABI_VERSION 1
+
+enum { KB200_F32 = 0, KB200_F64 = 1 };
+/* torch.nn.functional.grid_sample `mode` as forwarded by imgwarp.py:174,290,702 */
+enum { KB200_BILINEAR = 0, KB200_NEAREST = 1, KB200_BICUBIC = 2 };
+/* `padding_mode`; FILL is Kornia's own mode (imgwarp.py:172-173,293-320) */
+enum { KB200_ZEROS = 0, KB200_BORDER = 1, KB200_REFLECTION = 2, KB200_FILL = 3 };
+/* `border_type` of filter2d (filters/filter.py:26) */
+enum { KB200_CONSTANT = 0, KB200_REFLECT = 1, KB200_REPLICATE = 2, KB200_CIRCULAR = 3 };
+
+enum {
+  KB200_OK = 0,
+  KB200_EINVAL = -1,      /* bad argument (shape, enum, null pointer) */
+  KB200_ECUDA = -2,       /* a CUDA runtime / driver call failed */
+  KB200_EUNSUPPORTED = -3 /* valid request this build does not cover */
+};
+
+int kb200_abi_version(void);
+const char* kb200_last_error(void);
+/* Name of the device-code variant the last kb200_warp_forward call on this thread dispatched to
+ * ("tma_tile" or "generic"); for tests and the bench. */
+const char* kb200_last_warp_variant(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused projective / affine warp, forward.
+ * Replaces imgwarp.py:157-174 (warp_perspective: create_meshgrid + 15 elementwise kernels +
+ * stack + F.grid_sample) and imgwarp.py:277-290 (warp_affine), including _fill_and_warp
+ * (imgwarp.py:293-320) when pad == KB200_FILL.
+ *   src   (B,C,H,W)
+ *   m     (Bm,3,3)  src_norm <- dst_norm matrices (imgwarp.py:153,254); Bm == B, or 1 (shared)
+ *   bx,by (w),(h)   base-grid axes in [-1,1] (grid.py:65-78 / imgwarp.py:271-276)
+ *   fill  (C) or NULL; required iff pad == KB200_FILL
+ *   out   (B,C,h,w)
+ *   projective: 1 = divide by row 2 (imgwarp.py:167-169); 0 = affine rows only (:279-280)
+ * ------------------------------------------------------------------------------------------ */
+int kb200_warp_forward(const void* src, const void* m, const void* bx, const void* by, const void* fill,
+                       void* out, int B, int C, int H, int W, int h, int w, int Bm, int projective,
+                       int interp, int pad, int align_corners, int dtype, void* stream);
+
+/* Backward of the above w.r.t. src and m (replaces grid_sampler_2d_backward + the autograd of
+ * imgwarp.py:165-170).
+ *   gout (B,C,h,w) upstream gradient
+ *   gsrc (B,C,H,W) or NULL; MUST be zero-filled by the caller (scatter-add target)
+ *   gm   (Bm,3,3)  or NULL; fully overwritten (deterministic two-stage reduction)
+ *   workspace: kb200_warp_backward_workspace_bytes(...) bytes when gm != NULL, else may be NULL */
+size_t kb200_warp_backward_workspace_bytes(int B, int h, int w, int dtype);
+int kb200_warp_backward(const void* gout, const void* src, const void* m, const void* bx, const void* by,
+                        const void* fill, void* gsrc, void* gm, void* workspace, int B, int C, int H, int W,
+                        int h, int w, int Bm, int projective, int interp, int pad, int align_corners,
+                        int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * remap (imgwarp.py:681-702: stack + normalize_pixel_coordinates + expand + F.grid_sample).
+ *   map_x,map_y (Bmap,h,w), Bmap == B or 1; pixel coordinates unless normalized != 0
+ *   backward: gmap_x/gmap_y (B,h,w) per-sample (the caller sums over B when Bmap == 1), or NULL
+ * ------------------------------------------------------------------------------------------ */
+int kb200_remap_forward(const void* src, const void* map_x, const void* map_y, void* out, int B, int C, int H,
+                        int W, int h, int w, int Bmap, int normalized, int interp, int pad, int align_corners,
+                        int dtype, void* stream);
+int kb200_remap_backward(const void* gout, const void* src, const void* map_x, const void* map_y, void* gsrc,
+                         void* gmap_x, void* gmap_y, int B, int C, int H, int W, int h, int w, int Bmap,
+                         int normalized, int interp, int pad, int align_corners, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * filter2d core (filters/filter.py:136-150: F.pad + view + depthwise F.conv2d + view).
+ *   x      (B,C,H,W)
+ *   kernel (Bk,kh,kw) correlation taps, already flipped / normalised by the host
+ *          (filter.py:123-129); plane (b,c) uses kernel b mod Bk (filter.py:131,141-142)
+ *   same   1: 'same' (border-padded, out (B,C,H,W)); 0: 'valid' (out (B,C,H-kh+1,W-kw+1))
+ * Backward: gx = adjoint of pad+correlate applied to gout; gkernel (Bk,kh,kw) fully overwritten.
+ * ------------------------------------------------------------------------------------------ */
+int kb200_filter2d_forward(const void* x, const void* kernel, void* out, int B, int C, int H, int W, int Bk,
+                           int kh, int kw, int border, int same, int dtype, void* stream);
+int kb200_filter2d_backward_input(const void* gout, const void* kernel, void* gx, int B, int C, int H, int W,
+                                  int Bk, int kh, int kw, int border, int same, int dtype, void* stream);
+size_t kb200_filter2d_backward_kernel_workspace_bytes(int B, int C, int H, int W, int Bk, int kh, int kw, int dtype);
+int kb200_filter2d_backward_kernel(const void* gout, const void* x, void* gkernel, void* workspace, int B,
+                                   int C, int H, int W, int Bk, int kh, int kw, int border, int same,
+                                   int dtype, void* stream);
+
+/* filter2d_separable (filter.py:205-207) in ONE pass over HBM: row pass (1 x kw, kernel_x) then
+ * column pass (kh x 1, kernel_y) out of a shared-memory tile.  kernel_x (Bkx,kw), kernel_y (Bky,kh). */
+int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* kernel_y, void* out, int B, int C,
+                            int H, int W, int Bkx, int kw, int Bky, int kh, int border, int same, int dtype,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KORNIA_B200_H */

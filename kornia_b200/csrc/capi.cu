@@ -1,0 +1,421 @@
+// kornia_b200 -- extern "C" entry points (include/kornia_b200.h) and kernel dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "filter_generic.cuh"
+#include "warp_generic.cuh"
+#include "warp_tma.cuh"
+#include "sepfilter_tiled.cuh"
+
+namespace kb200 {
+
+static thread_local char g_err[512] = "";
+static thread_local const char* g_variant = "none";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int post_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+    return KB200_ECUDA;
+  }
+  return KB200_OK;
+}
+
+// blockIdx.z carries the sample / plane index; CUDA caps gridDim.z at 65535
+constexpr int MAX_Z = 65535;
+
+// ------------------------------------------------------------------------------------------
+// warp / remap dispatch
+// ------------------------------------------------------------------------------------------
+template <typename T, int INTERP, int PAD, int KIND>
+static int launch_warp_fwd(WarpParams<T> p, cudaStream_t st) {
+  const dim3 block(GEN_BX, GEN_BY);
+  const int B = p.B;
+  for (int b0 = 0; b0 < B; b0 += MAX_Z) {
+    WarpParams<T> q = p;
+    q.B = min(MAX_Z, B - b0);
+    q.src = p.src + (size_t)b0 * p.C * p.H * p.W;
+    q.out = p.out + (size_t)b0 * p.C * p.h * p.w;
+    if (KIND == KIND_REMAP) {
+      if (p.Bm != 1) {
+        q.map_x = p.map_x + (size_t)b0 * p.h * p.w;
+        q.map_y = p.map_y + (size_t)b0 * p.h * p.w;
+      }
+    } else if (p.Bm != 1) {
+      q.m = p.m + (size_t)b0 * 9;
+    }
+    const dim3 grid(ceil_div(p.w, GEN_BX), ceil_div(p.h, GEN_BY), q.B);
+    warp_fwd_generic<T, INTERP, PAD, KIND><<<grid, block, 0, st>>>(q);
+  }
+  return post_launch("warp_forward");
+}
+
+template <typename T, int INTERP, int PAD, int KIND>
+static int launch_warp_bwd(WarpGradParams<T> g, cudaStream_t st) {
+  const dim3 block(GEN_BX, GEN_BY);
+  const WarpParams<T>& p = g.p;
+  const int B = p.B;
+  const size_t nblk = (size_t)ceil_div(p.w, GEN_BX) * ceil_div(p.h, GEN_BY);
+  for (int b0 = 0; b0 < B; b0 += MAX_Z) {
+    WarpGradParams<T> q = g;
+    q.p.B = min(MAX_Z, B - b0);
+    q.p.src = p.src + (size_t)b0 * p.C * p.H * p.W;
+    q.gout = g.gout + (size_t)b0 * p.C * p.h * p.w;
+    if (g.gsrc) q.gsrc = g.gsrc + (size_t)b0 * p.C * p.H * p.W;
+    if (g.partial) q.partial = g.partial + (size_t)b0 * nblk * 9;
+    if (KIND == KIND_REMAP) {
+      if (p.Bm != 1) {
+        q.p.map_x = p.map_x + (size_t)b0 * p.h * p.w;
+        q.p.map_y = p.map_y + (size_t)b0 * p.h * p.w;
+      }
+      if (g.gmap_x) {
+        q.gmap_x = g.gmap_x + (size_t)b0 * p.h * p.w;
+        q.gmap_y = g.gmap_y + (size_t)b0 * p.h * p.w;
+      }
+    } else if (p.Bm != 1) {
+      q.p.m = p.m + (size_t)b0 * 9;
+    }
+    const dim3 grid(ceil_div(p.w, GEN_BX), ceil_div(p.h, GEN_BY), q.p.B);
+    warp_bwd_generic<T, INTERP, PAD, KIND><<<grid, block, 0, st>>>(q);
+  }
+  return post_launch("warp_backward");
+}
+
+#define KB_DISPATCH_PAD(T, INTERP, KIND, FN, ARG)                                     \
+  switch (pad) {                                                                      \
+    case KB200_ZEROS: return FN<T, INTERP, KB200_ZEROS, KIND>(ARG, st);               \
+    case KB200_BORDER: return FN<T, INTERP, KB200_BORDER, KIND>(ARG, st);             \
+    case KB200_REFLECTION: return FN<T, INTERP, KB200_REFLECTION, KIND>(ARG, st);     \
+    case KB200_FILL:                                                                  \
+      if (KIND == KIND_REMAP) break;                                                  \
+      return FN<T, INTERP, KB200_FILL, (KIND == KIND_REMAP ? KIND_AFFINE : KIND)>(ARG, st); \
+  }                                                                                   \
+  break;
+
+#define KB_DISPATCH_INTERP(T, KIND, FN, ARG)                                       \
+  switch (interp) {                                                                \
+    case KB200_BILINEAR: KB_DISPATCH_PAD(T, KB200_BILINEAR, KIND, FN, ARG)         \
+    case KB200_NEAREST: KB_DISPATCH_PAD(T, KB200_NEAREST, KIND, FN, ARG)           \
+    case KB200_BICUBIC: KB_DISPATCH_PAD(T, KB200_BICUBIC, KIND, FN, ARG)           \
+  }
+
+template <typename T, int KIND>
+static int dispatch_fwd(const WarpParams<T>& p, int interp, int pad, cudaStream_t st) {
+  KB_DISPATCH_INTERP(T, KIND, launch_warp_fwd, p)
+  set_error("unsupported interp=%d / pad=%d", interp, pad);
+  return KB200_EINVAL;
+}
+
+template <typename T, int KIND>
+static int dispatch_bwd(const WarpGradParams<T>& g, int interp, int pad, cudaStream_t st) {
+  KB_DISPATCH_INTERP(T, KIND, launch_warp_bwd, g)
+  set_error("unsupported interp=%d / pad=%d", interp, pad);
+  return KB200_EINVAL;
+}
+
+static int check_common(const void* src, int B, int C, int H, int W, int h, int w, int Bm, int interp, int pad, int dtype,
+                        bool allow_fill) {
+  KB_CHECK_ARG(src != nullptr, "null src");
+  KB_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && h > 0 && w > 0, "non-positive shape B=%d C=%d H=%d W=%d h=%d w=%d", B, C, H, W, h, w);
+  KB_CHECK_ARG((long long)H * W < (1ll << 31) && (long long)h * w < (1ll << 31), "plane too large for 32-bit in-plane offsets");
+  KB_CHECK_ARG(Bm == B || Bm == 1, "matrix/map batch %d must be %d or 1", Bm, B);
+  KB_CHECK_ARG(interp >= KB200_BILINEAR && interp <= KB200_BICUBIC, "bad interp %d", interp);
+  KB_CHECK_ARG(pad >= KB200_ZEROS && pad <= (allow_fill ? KB200_FILL : KB200_REFLECTION), "bad pad %d", pad);
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  return KB200_OK;
+}
+
+template <typename T>
+static int warp_forward_t(const void* src, const void* m, const void* bx, const void* by, const void* fill, void* out, int B,
+                          int C, int H, int W, int h, int w, int Bm, int projective, int interp, int pad, int align,
+                          cudaStream_t st) {
+  WarpParams<T> p{};
+  p.src = (const T*)src; p.m = (const T*)m; p.bx = (const T*)bx; p.by = (const T*)by;
+  p.fill = (const T*)fill; p.out = (T*)out;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = Bm; p.align = align; p.normalized = 0;
+  return projective ? dispatch_fwd<T, KIND_PROJ>(p, interp, pad, st) : dispatch_fwd<T, KIND_AFFINE>(p, interp, pad, st);
+}
+
+}  // namespace kb200
+
+using namespace kb200;
+
+// The prototypes in include/kornia_b200.h are extern "C"; the definitions below inherit that linkage.
+
+int kb200_abi_version(void) { return KB200_ABI_VERSION; }
+const char* kb200_last_error(void) { return g_err; }
+const char* kb200_last_warp_variant(void) { return g_variant; }
+
+int kb200_warp_forward(const void* src, const void* m, const void* bx, const void* by, const void* fill, void* out, int B,
+                       int C, int H, int W, int h, int w, int Bm, int projective, int interp, int pad, int align_corners,
+                       int dtype, void* stream) {
+  int rc = check_common(src, B, C, H, W, h, w, Bm, interp, pad, dtype, true);
+  if (rc) return rc;
+  KB_CHECK_ARG(m && bx && by && out, "null pointer argument");
+  KB_CHECK_ARG(pad != KB200_FILL || fill, "pad=fill needs a fill vector");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == KB200_F32) {
+    // fast path: TMA-staged source tiles (warp_tma.cuh); declines shapes / modes it does not cover
+    rc = warp_tma_forward((const float*)src, (const float*)m, (const float*)bx, (const float*)by, (const float*)fill,
+                          (float*)out, B, C, H, W, h, w, Bm, projective, interp, pad, align_corners, st);
+    if (rc != KB200_EUNSUPPORTED) {
+      g_variant = "tma_tile";
+      return rc;
+    }
+    g_variant = "generic";
+    return warp_forward_t<float>(src, m, bx, by, fill, out, B, C, H, W, h, w, Bm, projective, interp, pad, align_corners, st);
+  }
+  g_variant = "generic";
+  return warp_forward_t<double>(src, m, bx, by, fill, out, B, C, H, W, h, w, Bm, projective, interp, pad, align_corners, st);
+}
+
+size_t kb200_warp_backward_workspace_bytes(int B, int h, int w, int dtype) {
+  const size_t nblk = (size_t)ceil_div(w, GEN_BX) * ceil_div(h, GEN_BY);
+  return (size_t)B * nblk * 9 * (dtype == KB200_F64 ? 8 : 4);
+}
+
+template <typename T>
+static int warp_backward_t(const void* gout, const void* src, const void* m, const void* bx, const void* by, const void* fill,
+                           void* gsrc, void* gm, void* workspace, int B, int C, int H, int W, int h, int w, int Bm,
+                           int projective, int interp, int pad, int align, cudaStream_t st) {
+  WarpGradParams<T> g{};
+  g.p.src = (const T*)src; g.p.m = (const T*)m; g.p.bx = (const T*)bx; g.p.by = (const T*)by; g.p.fill = (const T*)fill;
+  g.p.B = B; g.p.C = C; g.p.H = H; g.p.W = W; g.p.h = h; g.p.w = w; g.p.Bm = Bm; g.p.align = align;
+  g.gout = (const T*)gout; g.gsrc = (T*)gsrc; g.partial = gm ? (T*)workspace : nullptr;
+  g.need_coord_grad = gm != nullptr;
+  int rc = projective ? dispatch_bwd<T, KIND_PROJ>(g, interp, pad, st) : dispatch_bwd<T, KIND_AFFINE>(g, interp, pad, st);
+  if (rc || !gm) return rc;
+  const long long nblk = (long long)ceil_div(w, GEN_BX) * ceil_div(h, GEN_BY);
+  warp_gm_reduce<T><<<dim3(9, Bm), 256, 0, st>>>((const T*)workspace, (T*)gm, B, Bm, nblk);
+  return post_launch("warp_gm_reduce");
+}
+
+int kb200_warp_backward(const void* gout, const void* src, const void* m, const void* bx, const void* by, const void* fill,
+                        void* gsrc, void* gm, void* workspace, int B, int C, int H, int W, int h, int w, int Bm,
+                        int projective, int interp, int pad, int align_corners, int dtype, void* stream) {
+  int rc = check_common(src, B, C, H, W, h, w, Bm, interp, pad, dtype, true);
+  if (rc) return rc;
+  KB_CHECK_ARG(gout && m && bx && by, "null pointer argument");
+  KB_CHECK_ARG(gsrc || gm, "nothing to compute: both gsrc and gm are null");
+  KB_CHECK_ARG(!gm || workspace, "gm requested without workspace");
+  KB_CHECK_ARG(pad != KB200_FILL || fill, "pad=fill needs a fill vector");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == KB200_F32)
+    return warp_backward_t<float>(gout, src, m, bx, by, fill, gsrc, gm, workspace, B, C, H, W, h, w, Bm, projective, interp,
+                                  pad, align_corners, st);
+  return warp_backward_t<double>(gout, src, m, bx, by, fill, gsrc, gm, workspace, B, C, H, W, h, w, Bm, projective, interp,
+                                 pad, align_corners, st);
+}
+
+template <typename T>
+static int remap_forward_t(const void* src, const void* mx, const void* my, void* out, int B, int C, int H, int W, int h, int w,
+                           int Bmap, int normalized, int interp, int pad, int align, cudaStream_t st) {
+  WarpParams<T> p{};
+  p.src = (const T*)src; p.map_x = (const T*)mx; p.map_y = (const T*)my; p.out = (T*)out;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = Bmap; p.align = align; p.normalized = normalized;
+  return dispatch_fwd<T, KIND_REMAP>(p, interp, pad, st);
+}
+
+int kb200_remap_forward(const void* src, const void* map_x, const void* map_y, void* out, int B, int C, int H, int W, int h,
+                        int w, int Bmap, int normalized, int interp, int pad, int align_corners, int dtype, void* stream) {
+  int rc = check_common(src, B, C, H, W, h, w, Bmap, interp, pad, dtype, false);
+  if (rc) return rc;
+  KB_CHECK_ARG(map_x && map_y && out, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == KB200_F32)
+    return remap_forward_t<float>(src, map_x, map_y, out, B, C, H, W, h, w, Bmap, normalized, interp, pad, align_corners, st);
+  return remap_forward_t<double>(src, map_x, map_y, out, B, C, H, W, h, w, Bmap, normalized, interp, pad, align_corners, st);
+}
+
+template <typename T>
+static int remap_backward_t(const void* gout, const void* src, const void* mx, const void* my, void* gsrc, void* gmx, void* gmy,
+                            int B, int C, int H, int W, int h, int w, int Bmap, int normalized, int interp, int pad, int align,
+                            cudaStream_t st) {
+  WarpGradParams<T> g{};
+  g.p.src = (const T*)src; g.p.map_x = (const T*)mx; g.p.map_y = (const T*)my;
+  g.p.B = B; g.p.C = C; g.p.H = H; g.p.W = W; g.p.h = h; g.p.w = w; g.p.Bm = Bmap; g.p.align = align;
+  g.p.normalized = normalized;
+  g.gout = (const T*)gout; g.gsrc = (T*)gsrc; g.gmap_x = (T*)gmx; g.gmap_y = (T*)gmy;
+  g.need_coord_grad = gmx != nullptr;
+  return dispatch_bwd<T, KIND_REMAP>(g, interp, pad, st);
+}
+
+int kb200_remap_backward(const void* gout, const void* src, const void* map_x, const void* map_y, void* gsrc, void* gmap_x,
+                         void* gmap_y, int B, int C, int H, int W, int h, int w, int Bmap, int normalized, int interp, int pad,
+                         int align_corners, int dtype, void* stream) {
+  int rc = check_common(src, B, C, H, W, h, w, Bmap, interp, pad, dtype, false);
+  if (rc) return rc;
+  KB_CHECK_ARG(gout && map_x && map_y, "null pointer argument");
+  KB_CHECK_ARG((gmap_x == nullptr) == (gmap_y == nullptr), "gmap_x and gmap_y must be given together");
+  KB_CHECK_ARG(gsrc || gmap_x, "nothing to compute");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == KB200_F32)
+    return remap_backward_t<float>(gout, src, map_x, map_y, gsrc, gmap_x, gmap_y, B, C, H, W, h, w, Bmap, normalized, interp, pad,
+                                   align_corners, st);
+  return remap_backward_t<double>(gout, src, map_x, map_y, gsrc, gmap_x, gmap_y, B, C, H, W, h, w, Bmap, normalized, interp, pad,
+                                  align_corners, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// filters
+// ------------------------------------------------------------------------------------------
+static int check_filter(const void* x, const void* k, int B, int C, int H, int W, int Bk, int kh, int kw, int border, int same,
+                        int dtype) {
+  KB_CHECK_ARG(x && k, "null pointer argument");
+  KB_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && Bk > 0 && kh > 0 && kw > 0, "non-positive shape");
+  KB_CHECK_ARG(B % Bk == 0, "kernel batch %d must divide the input batch %d", Bk, B);
+  KB_CHECK_ARG((long long)H * W < (1ll << 31), "plane too large");
+  KB_CHECK_ARG(border >= KB200_CONSTANT && border <= KB200_CIRCULAR, "bad border %d", border);
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  if (same) {
+    const int ph = kh - 1 - (kh - 1) / 2, pw = kw - 1 - (kw - 1) / 2;  // the larger (rear) pad
+    if (border == KB200_REFLECT) KB_CHECK_ARG(ph < H && pw < W, "reflect padding (%d,%d) must be smaller than the image (%d,%d)", ph, pw, H, W);
+    if (border == KB200_CIRCULAR) KB_CHECK_ARG(ph <= H && pw <= W, "circular padding (%d,%d) must not exceed the image (%d,%d)", ph, pw, H, W);
+  } else {
+    KB_CHECK_ARG(kh <= H && kw <= W, "'valid' needs kernel (%d,%d) <= image (%d,%d)", kh, kw, H, W);
+  }
+  return KB200_OK;
+}
+
+template <typename T>
+static FilterParams<T> make_fp(const void* x, const void* k, void* out, int B, int C, int H, int W, int Bk, int kh, int kw,
+                               int same) {
+  FilterParams<T> p{};
+  p.x = (const T*)x; p.k = (const T*)k; p.out = (T*)out;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.Bk = Bk; p.kh = kh; p.kw = kw;
+  p.top = same ? (kh - 1) / 2 : 0;
+  p.left = same ? (kw - 1) / 2 : 0;
+  p.Ho = same ? H : H - kh + 1;
+  p.Wo = same ? W : W - kw + 1;
+  return p;
+}
+
+#define KB_BORDER_SWITCH(border, same, ...)                   \
+  switch ((same) ? (border) : KB200_CONSTANT) {                \
+    case KB200_CONSTANT: { constexpr int BD = KB200_CONSTANT; __VA_ARGS__; break; }   \
+    case KB200_REFLECT: { constexpr int BD = KB200_REFLECT; __VA_ARGS__; break; }     \
+    case KB200_REPLICATE: { constexpr int BD = KB200_REPLICATE; __VA_ARGS__; break; } \
+    case KB200_CIRCULAR: { constexpr int BD = KB200_CIRCULAR; __VA_ARGS__; break; }   \
+  }
+
+template <typename T>
+static int filter2d_forward_t(const void* x, const void* k, void* out, int B, int C, int H, int W, int Bk, int kh, int kw,
+                              int border, int same, cudaStream_t st) {
+  FilterParams<T> p = make_fp<T>(x, k, out, B, C, H, W, Bk, kh, kw, same);
+  const dim3 grid(ceil_div(p.Wo, 32), ceil_div(p.Ho, 8), B * C);
+  KB_BORDER_SWITCH(border, same, (filter2d_fwd_generic<T, BD><<<grid, dim3(32, 8), 0, st>>>(p)));
+  return post_launch("filter2d_forward");
+}
+
+int kb200_filter2d_forward(const void* x, const void* kernel, void* out, int B, int C, int H, int W, int Bk, int kh, int kw,
+                           int border, int same, int dtype, void* stream) {
+  int rc = check_filter(x, kernel, B, C, H, W, Bk, kh, kw, border, same, dtype);
+  if (rc) return rc;
+  KB_CHECK_ARG(out, "null out");
+  KB_CHECK_ARG((long long)B * C <= MAX_Z, "B*C = %lld planes exceed the %d-plane launch limit", (long long)B * C, MAX_Z);
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == KB200_F32 ? filter2d_forward_t<float>(x, kernel, out, B, C, H, W, Bk, kh, kw, border, same, st)
+                            : filter2d_forward_t<double>(x, kernel, out, B, C, H, W, Bk, kh, kw, border, same, st);
+}
+
+template <typename T>
+static int filter2d_backward_input_t(const void* gout, const void* k, void* gx, int B, int C, int H, int W, int Bk, int kh,
+                                     int kw, int border, int same, cudaStream_t st) {
+  FilterParams<T> p = make_fp<T>(nullptr, k, nullptr, B, C, H, W, Bk, kh, kw, same);
+  const int bottom = same ? (kh - 1) - p.top : 0, right = same ? (kw - 1) - p.left : 0;
+  const dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B * C);
+  KB_BORDER_SWITCH(border, same,
+                   (filter2d_bwd_input_generic<T, BD><<<grid, dim3(32, 8), 0, st>>>(p, (const T*)gout, (T*)gx, bottom, right)));
+  return post_launch("filter2d_backward_input");
+}
+
+int kb200_filter2d_backward_input(const void* gout, const void* kernel, void* gx, int B, int C, int H, int W, int Bk, int kh,
+                                  int kw, int border, int same, int dtype, void* stream) {
+  int rc = check_filter(gout, kernel, B, C, H, W, Bk, kh, kw, border, same, dtype);
+  if (rc) return rc;
+  KB_CHECK_ARG(gx, "null gx");
+  KB_CHECK_ARG((long long)B * C <= MAX_Z, "B*C = %lld planes exceed the %d-plane launch limit", (long long)B * C, MAX_Z);
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == KB200_F32 ? filter2d_backward_input_t<float>(gout, kernel, gx, B, C, H, W, Bk, kh, kw, border, same, st)
+                            : filter2d_backward_input_t<double>(gout, kernel, gx, B, C, H, W, Bk, kh, kw, border, same, st);
+}
+
+size_t kb200_filter2d_backward_kernel_workspace_bytes(int B, int C, int H, int W, int Bk, int kh, int kw, int dtype) {
+  (void)H; (void)W; (void)Bk;
+  return (size_t)B * C * kh * kw * (dtype == KB200_F64 ? 8 : 4);
+}
+
+template <typename T>
+static int filter2d_backward_kernel_t(const void* gout, const void* x, void* gk, void* ws, int B, int C, int H, int W, int Bk,
+                                      int kh, int kw, int border, int same, cudaStream_t st) {
+  FilterParams<T> p = make_fp<T>(x, nullptr, nullptr, B, C, H, W, Bk, kh, kw, same);
+  const dim3 grid(kh * kw, B * C);
+  KB_BORDER_SWITCH(border, same, (filter2d_bwd_kernel_stage1<T, BD><<<grid, 256, 0, st>>>(p, (const T*)gout, (T*)ws)));
+  int rc = post_launch("filter2d_backward_kernel stage1");
+  if (rc) return rc;
+  const int taps = kh * kw;
+  filter2d_bwd_kernel_stage2<T><<<dim3(ceil_div(taps, 128), Bk), 128, 0, st>>>((const T*)ws, (T*)gk, B, C, Bk, taps);
+  return post_launch("filter2d_backward_kernel stage2");
+}
+
+int kb200_filter2d_backward_kernel(const void* gout, const void* x, void* gkernel, void* workspace, int B, int C, int H, int W,
+                                   int Bk, int kh, int kw, int border, int same, int dtype, void* stream) {
+  int rc = check_filter(x, gout, B, C, H, W, Bk, kh, kw, border, same, dtype);
+  if (rc) return rc;
+  KB_CHECK_ARG(gkernel && workspace, "null gkernel / workspace");
+  KB_CHECK_ARG((long long)B * C <= MAX_Z && kh * kw <= 65535 * 32, "launch limits exceeded");
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == KB200_F32
+             ? filter2d_backward_kernel_t<float>(gout, x, gkernel, workspace, B, C, H, W, Bk, kh, kw, border, same, st)
+             : filter2d_backward_kernel_t<double>(gout, x, gkernel, workspace, B, C, H, W, Bk, kh, kw, border, same, st);
+}
+
+template <typename T>
+static int sepfilter_forward_t(const void* x, const void* kx, const void* ky, void* out, int B, int C, int H, int W, int Bkx,
+                               int kw, int Bky, int kh, int border, int same, cudaStream_t st) {
+  SepParams<T> p{};
+  p.x = (const T*)x; p.kx = (const T*)kx; p.ky = (const T*)ky; p.out = (T*)out;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.Bkx = Bkx; p.kw = kw; p.Bky = Bky; p.kh = kh;
+  p.top = same ? (kh - 1) / 2 : 0;
+  p.left = same ? (kw - 1) / 2 : 0;
+  p.Ho = same ? H : H - kh + 1;
+  p.Wo = same ? W : W - kw + 1;
+  const int in_w = SEP_TW + kw - 1, in_h = SEP_TH + kh - 1;
+  const size_t smem = ((size_t)in_h * in_w + (size_t)in_h * SEP_TW + kw + kh) * sizeof(T);
+  if (smem > 200 * 1024) {
+    set_error("separable kernel (%d,%d) needs %zu B of shared memory; use two filter2d passes", kh, kw, smem);
+    return KB200_EUNSUPPORTED;
+  }
+  const dim3 grid(ceil_div(p.Wo, SEP_TW), ceil_div(p.Ho, SEP_TH), B * C);
+  KB_BORDER_SWITCH(border, same, {
+    auto kern = sepfilter_fwd_generic<T, BD>;
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(p);
+  });
+  return post_launch("sepfilter_forward");
+}
+
+int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* kernel_y, void* out, int B, int C, int H, int W,
+                            int Bkx, int kw, int Bky, int kh, int border, int same, int dtype, void* stream) {
+  int rc = check_filter(x, kernel_x, B, C, H, W, Bkx, kh, kw, border, same, dtype);
+  if (rc) return rc;
+  KB_CHECK_ARG(kernel_y && out, "null pointer argument");
+  KB_CHECK_ARG(Bky > 0 && B % Bky == 0, "kernel_y batch %d must divide the input batch %d", Bky, B);
+  KB_CHECK_ARG((long long)B * C <= MAX_Z, "B*C = %lld planes exceed the %d-plane launch limit", (long long)B * C, MAX_Z);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == KB200_F32) {
+    rc = sepfilter_tiled_forward((const float*)x, (const float*)kernel_x, (const float*)kernel_y, (float*)out, B, C, H, W, Bkx,
+                                 kw, Bky, kh, border, same, st);
+    if (rc != KB200_EUNSUPPORTED) return rc;
+    return sepfilter_forward_t<float>(x, kernel_x, kernel_y, out, B, C, H, W, Bkx, kw, Bky, kh, border, same, st);
+  }
+  return sepfilter_forward_t<double>(x, kernel_x, kernel_y, out, B, C, H, W, Bkx, kw, Bky, kh, border, same, st);
+}
+
