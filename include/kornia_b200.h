@@ -112,6 +112,13 @@ int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* ker
                             int H, int W, int Bkx, int kw, int Bky, int kh, int border, int same, int dtype,
                             void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics (used by tests/): counts elements where the shared-reciprocal division of the tiled
+ * warp kernel differs from IEEE division in a way that could change a sampled pixel.  `count`
+ * (device int, zeroed by the caller) is incremented atomically.
+ * ------------------------------------------------------------------------------------------ */
+int kb200_debug_fastdiv_mismatches(const float* num, const float* den, int n, int* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

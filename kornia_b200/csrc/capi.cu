@@ -1,5 +1,6 @@
 // kornia_b200 -- extern "C" entry points (include/kornia_b200.h) and kernel dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "filter_generic.cuh"
@@ -162,8 +163,10 @@ int kb200_warp_forward(const void* src, const void* m, const void* bx, const voi
   KB_CHECK_ARG(pad != KB200_FILL || fill, "pad=fill needs a fill vector");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == KB200_F32) {
-    // fast path: TMA-staged source tiles (warp_tma.cuh); declines shapes / modes it does not cover
-    rc = warp_tma_forward((const float*)src, (const float*)m, (const float*)bx, (const float*)by, (const float*)fill,
+    // fast path: TMA-staged source tiles (warp_tma.cuh); declines shapes / modes it does not cover.
+    // KB200_DISABLE_TMA=1 forces the generic kernel (tests compare the two bit for bit).
+    const char* off = getenv("KB200_DISABLE_TMA");
+    rc = (off && off[0] == '1') ? KB200_EUNSUPPORTED : warp_tma_forward((const float*)src, (const float*)m, (const float*)bx, (const float*)by, (const float*)fill,
                           (float*)out, B, C, H, W, h, w, Bm, projective, interp, pad, align_corners, st);
     if (rc != KB200_EUNSUPPORTED) {
       g_variant = "tma_tile";
@@ -419,3 +422,27 @@ int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* ker
   return sepfilter_forward_t<double>(x, kernel_x, kernel_y, out, B, C, H, W, Bkx, kw, Bky, kh, border, same, st);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------------
+namespace kb200 {
+__global__ void fastdiv_check_kernel(const float* __restrict__ num, const float* __restrict__ den, int n, int* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = num[i], b = den[i];
+  if (!(fabsf(b) >= 8.67361738e-19f)) return;  // outside the window the kernel uses __fdiv_rn itself
+  const float q = div_by_rcp(a, b, refined_rcp(b));
+  const float want = __fdiv_rn(a, b);
+  // NaN == NaN for this purpose; differing non-finite / sub-2^-24 results cannot change a sampled pixel
+  const bool same = (__float_as_uint(q) == __float_as_uint(want)) || (q != q && want != want) ||
+                    (!(fabsf(want) <= 3.0e38f) && !(fabsf(q) <= 3.0e38f)) || (fabsf(want) < 5.9e-8f && fabsf(q) < 5.9e-8f);
+  if (!same) atomicAdd(bad, 1);
+}
+}  // namespace kb200
+
+int kb200_debug_fastdiv_mismatches(const float* num, const float* den, int n, int* count, void* stream) {
+  KB_CHECK_ARG(num && den && count && n > 0, "bad arguments");
+  fastdiv_check_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(num, den, n, count);
+  return post_launch("fastdiv_check");
+}
