@@ -65,6 +65,14 @@ int kb200_warp_forward(const void* src, const void* m, const void* bx, const voi
                        void* out, int B, int C, int H, int W, int h, int w, int Bm, int projective,
                        int interp, int pad, int align_corners, int dtype, void* stream);
 
+/* (B,3,3) prelude in one launch: m_out = inverse(N_dst @ (M3 @ inverse(N_src))) with N the pixel->[-1,1]
+ * matrices of (H,W) and (h,w) (conversions.py:1717-1725,1753-1765; core/utils.py:159-166) and M3 = M for
+ * rows == 3 or M padded with [0,0,1] for rows == 2 (conversions.py:342-345).  Bit-identical to the torch op
+ * sequence on the same device for variant 0 (pinned by the GPU tests); not differentiable -- callers that
+ * need d/dM keep the torch ops. */
+int kb200_warp_prelude(const void* M, void* m_out, int B, int rows, int H, int W, int h, int w, int dtype,
+                       int variant, void* stream);
+
 /* Backward of the above w.r.t. src and m (replaces grid_sampler_2d_backward + the autograd of
  * imgwarp.py:165-170).
  *   gout (B,C,h,w) upstream gradient

@@ -31,6 +31,7 @@ SIGNATURES = {
     "kb200_last_error": (ctypes.c_char_p, []),
     "kb200_last_warp_variant": (ctypes.c_char_p, []),
     "kb200_warp_forward": (_i, [_vp] * 6 + [_i] * 12 + [_vp]),
+    "kb200_warp_prelude": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),
     "kb200_warp_backward_workspace_bytes": (_sz, [_i] * 4),
     "kb200_warp_backward": (_i, [_vp] * 9 + [_i] * 12 + [_vp]),
     "kb200_remap_forward": (_i, [_vp] * 4 + [_i] * 12 + [_vp]),

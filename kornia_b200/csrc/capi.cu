@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "filter_generic.cuh"
+#include "prelude.cuh"
 #include "warp_generic.cuh"
 #include "warp_tma.cuh"
 #include "sepfilter_tiled.cuh"
@@ -422,6 +423,24 @@ int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* ker
   return sepfilter_forward_t<double>(x, kernel_x, kernel_y, out, B, C, H, W, Bkx, kw, Bky, kh, border, same, st);
 }
 
+
+int kb200_warp_prelude(const void* M, void* m_out, int B, int rows, int H, int W, int h, int w, int dtype, int variant,
+                       void* stream) {
+  KB_CHECK_ARG(M && m_out && B > 0, "bad arguments");
+  KB_CHECK_ARG(rows == 2 || rows == 3, "rows must be 2 (affine) or 3 (projective), got %d", rows);
+  KB_CHECK_ARG(H > 0 && W > 0 && h > 0 && w > 0, "non-positive size");
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  // normal_transform_pixel (conversions.py:1753-1765): python floats -> fp32 tensor -> cast to M's dtype
+  const float sx_s = (float)(2.0 / (W == 1 ? 1e-14 : (double)W - 1.0)), sy_s = (float)(2.0 / (H == 1 ? 1e-14 : (double)H - 1.0));
+  const float sx_d = (float)(2.0 / (w == 1 ? 1e-14 : (double)w - 1.0)), sy_d = (float)(2.0 / (h == 1 ? 1e-14 : (double)h - 1.0));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(B, 128);
+  if (dtype == KB200_F32)
+    warp_prelude_kernel<float><<<grid, 128, 0, st>>>((const float*)M, (float*)m_out, B, rows, sx_s, sy_s, sx_d, sy_d, variant);
+  else
+    warp_prelude_kernel<double><<<grid, 128, 0, st>>>((const double*)M, (double*)m_out, B, rows, sx_s, sy_s, sx_d, sy_d, variant);
+  return post_launch("warp_prelude");
+}
 
 // ------------------------------------------------------------------------------------------
 // diagnostics

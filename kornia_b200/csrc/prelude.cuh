@@ -1,0 +1,85 @@
+// kornia_b200 -- fused (B,3,3) prelude: m = inverse( N_dst @ (M @ inverse(N_src)) ).
+//
+// Replaces the ~35 tiny torch launches of normalize_homography + _inverse_3x3_closed_form
+// (kornia/geometry/conversions.py:1717-1725, kornia/core/utils.py:159-166) with one launch when no
+// gradient w.r.t. M is needed.  The arithmetic mimics what those torch CUDA kernels compute, so the
+// result is bit-identical to the torch prelude on the same device (asserted by
+// tests/test_parity_gpu.py::test_fused_prelude_bit_identical; the host layer falls back to the
+// torch ops when M requires grad).  `variant` selects between plausible contraction orders of the
+// third-party kernels; the test pins the one that matches.
+#pragma once
+#include "common.cuh"
+
+namespace kb200 {
+
+template <typename T>
+__device__ __forceinline__ T cross_term(T a, T b, T c, T d, int variant) {  // a*b - c*d as at::cross_kernel rounds it
+  using R = RN<T>;
+  if (variant & 1) return R::fma(-c, d, R::mul(a, b));
+  return R::fma(a, b, -R::mul(c, d));
+}
+
+template <typename T>
+__device__ __forceinline__ void inv3_torchlike(const T A[9], T out[9], int variant) {
+  using R = RN<T>;
+  // columns a, b, c ; rows of the adjugate are b x c, c x a, a x b  (utils.py:159-164)
+  const T a0 = A[0], a1 = A[3], a2 = A[6];
+  const T b0 = A[1], b1 = A[4], b2 = A[7];
+  const T c0 = A[2], c1 = A[5], c2 = A[8];
+  T r[9];
+  r[0] = cross_term(b1, c2, b2, c1, variant); r[1] = cross_term(b2, c0, b0, c2, variant); r[2] = cross_term(b0, c1, b1, c0, variant);
+  r[3] = cross_term(c1, a2, c2, a1, variant); r[4] = cross_term(c2, a0, c0, a2, variant); r[5] = cross_term(c0, a1, c1, a0, variant);
+  r[6] = cross_term(a1, b2, a2, b1, variant); r[7] = cross_term(a2, b0, a0, b2, variant); r[8] = cross_term(a0, b1, a1, b0, variant);
+  // det = (col_a * row0).sum(-1): products rounded by the mul kernel, then summed left to right
+  const T p0 = R::mul(a0, r[0]), p1 = R::mul(a1, r[1]), p2 = R::mul(a2, r[2]);
+  T det;
+  if (variant & 4) det = R::add(R::add(p0, p2), p1);       // strided two-lane reduction: (x0 + x2) + x1
+  else if (variant & 8) det = R::add(p0, R::add(p1, p2));
+  else det = R::add(R::add(p0, p1), p2);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[i] = R::div(r[i], det);
+}
+
+template <typename T>
+__device__ __forceinline__ void matmul3_torchlike(const T A[9], const T Bm[9], T C[9], int variant) {
+  using R = RN<T>;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      T acc;
+      if (variant & 2) {
+        acc = R::add(R::add(R::mul(A[i * 3], Bm[j]), R::mul(A[i * 3 + 1], Bm[3 + j])), R::mul(A[i * 3 + 2], Bm[6 + j]));
+      } else {  // GEMM inner loop: fused multiply-add over k, accumulator starts at zero
+        acc = R::fma(A[i * 3], Bm[j], T(0));
+        acc = R::fma(A[i * 3 + 1], Bm[3 + j], acc);
+        acc = R::fma(A[i * 3 + 2], Bm[6 + j], acc);
+      }
+      C[i * 3 + j] = acc;
+    }
+}
+
+template <typename T>
+__global__ void warp_prelude_kernel(const T* __restrict__ M, T* __restrict__ out, int B, int rows, float sx_s, float sy_s,
+                                    float sx_d, float sy_d, int variant) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  T Mh[9];
+  for (int i = 0; i < rows * 3; ++i) Mh[i] = M[(size_t)b * rows * 3 + i];
+  if (rows == 2) {  // convert_affinematrix_to_homography: pad a zero row, then += 1 on the corner
+    Mh[6] = T(0);
+    Mh[7] = T(0);
+    Mh[8] = RN<T>::add(T(0), T(1));
+  }
+  const T Ns[9] = {T(sx_s), T(0), T(-1), T(0), T(sy_s), T(-1), T(0), T(0), T(1)};
+  const T Nd[9] = {T(sx_d), T(0), T(-1), T(0), T(sy_d), T(-1), T(0), T(0), T(1)};
+  T Nsi[9], X[9], Mn[9], m[9];
+  inv3_torchlike<T>(Ns, Nsi, variant);
+  matmul3_torchlike<T>(Mh, Nsi, X, variant);
+  matmul3_torchlike<T>(Nd, X, Mn, variant);
+  inv3_torchlike<T>(Mn, m, variant);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[(size_t)b * 9 + i] = m[i];
+}
+
+}  // namespace kb200

@@ -46,18 +46,70 @@ def affine_to_homography(A: torch.Tensor) -> torch.Tensor:
     return Hm
 
 
+# The base-grid axes depend only on (h, w, device, dtype): built once with the reference's own torch ops
+# (so they are bit-identical to what create_meshgrid / linspace produce on that device) and reused.
+_AXES_CACHE: dict = {}
+_AXES_CACHE_MAX = 64
+
+
+def _cached(key, build):
+    hit = _AXES_CACHE.get(key)
+    if hit is None:
+        if len(_AXES_CACHE) >= _AXES_CACHE_MAX:
+            _AXES_CACHE.clear()
+        hit = _AXES_CACHE[key] = build()
+    return hit
+
+
 def meshgrid_axes(h: int, w: int, device, dtype):
     """The two axes of create_meshgrid(normalized=True): built in fp32, then cast (imgwarp.py:157)."""
-    xs = torch.linspace(0, w - 1, w, device=device)
-    ys = torch.linspace(0, h - 1, h, device=device)
-    xs = (xs / (w - 1) - 0.5) * 2
-    ys = (ys / (h - 1) - 0.5) * 2
-    return xs.to(dtype), ys.to(dtype)
+
+    def build():
+        xs = torch.linspace(0, w - 1, w, device=device)
+        ys = torch.linspace(0, h - 1, h, device=device)
+        xs = (xs / (w - 1) - 0.5) * 2
+        ys = (ys / (h - 1) - 0.5) * 2
+        return xs.to(dtype), ys.to(dtype)
+
+    return _cached(("mesh", h, w, str(device), dtype), build)
 
 
 def affine_axes(h: int, w: int, align_corners: bool, device, dtype):
-    if align_corners:
-        return (torch.linspace(-1.0, 1.0, w, device=device, dtype=dtype),
-                torch.linspace(-1.0, 1.0, h, device=device, dtype=dtype))
-    return (torch.linspace(-1.0 + 1.0 / w, 1.0 - 1.0 / w, w, device=device, dtype=dtype),
-            torch.linspace(-1.0 + 1.0 / h, 1.0 - 1.0 / h, h, device=device, dtype=dtype))
+    def build():
+        if align_corners:
+            return (torch.linspace(-1.0, 1.0, w, device=device, dtype=dtype),
+                    torch.linspace(-1.0, 1.0, h, device=device, dtype=dtype))
+        return (torch.linspace(-1.0 + 1.0 / w, 1.0 - 1.0 / w, w, device=device, dtype=dtype),
+                torch.linspace(-1.0 + 1.0 / h, 1.0 - 1.0 / h, h, device=device, dtype=dtype))
+
+    return _cached(("affine", h, w, bool(align_corners), str(device), dtype), build)
+
+
+# ---------------------------------------------------------------------------------------------
+# one-launch prelude (kb200_warp_prelude) for the common no-grad-on-M case
+# ---------------------------------------------------------------------------------------------
+FUSED_VARIANT = 4       # the contraction orders that reproduce torch's CUDA kernels bit for bit (GPU-tested)
+FUSED_MIN_BATCH = 2     # below this torch's bmm takes a different (gemv-like) path; keep the torch ops there
+
+
+def sampling_matrix(M: torch.Tensor, src_hw, dst_hw, affine: bool) -> torch.Tensor:
+    """inverse(normalize_homography(M3)) -- the (B,3,3) dst-normalised -> src-normalised map the kernels
+    consume.  One CUDA launch when M is a plain CUDA fp32/fp64 tensor without grad; the reference's torch
+    op sequence (differentiable, same numbers) otherwise, or when KORNIA_B200_TORCH_PRELUDE=1."""
+    import os
+
+    fused_ok = (M.is_cuda and M.dtype in (torch.float32, torch.float64) and not (M.requires_grad and torch.is_grad_enabled())
+                and M.shape[0] >= FUSED_MIN_BATCH and os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") != "1")
+    if not fused_ok:
+        M3 = affine_to_homography(M) if affine else M
+        return inverse3x3(normalize_homography(M3, src_hw, dst_hw))
+    from .. import _lib, _ops
+
+    Mc = M.detach().contiguous()
+    out = torch.empty((Mc.shape[0], 3, 3), device=M.device, dtype=M.dtype)
+    with torch.cuda.device(M.device):
+        _lib.call("kb200_warp_prelude", Mc.data_ptr(), out.data_ptr(), Mc.shape[0], 2 if affine else 3, int(src_hw[0]), int(src_hw[1]),
+                  int(dst_hw[0]), int(dst_hw[1]), 0 if M.dtype == torch.float32 else 1, FUSED_VARIANT,
+                  torch.cuda.current_stream(M.device).cuda_stream)
+    _ops._bump()
+    return out

@@ -69,7 +69,7 @@ def warp_perspective(
         raise RuntimeError(f"grid_sampler(): expected grid and input to have same batch size, but got input with sizes "
                            f"{list(src.shape)} and grid with sizes {[M.shape[0], h_out, w_out, 2]}")
     # (B,3,3) prelude, identical op sequence to imgwarp.py:147-153
-    m = P.inverse3x3(P.normalize_homography(M, (H, W), (h_out, w_out)))
+    m = P.sampling_matrix(M, (H, W), (h_out, w_out), affine=False)
     bx, by = P.meshgrid_axes(h_out, w_out, src.device, src.dtype)
     fill = None
     if pad == _lib.FILL:
@@ -108,8 +108,9 @@ def warp_affine(
 
     B, C, H, W = src.shape
     h_out, w_out = int(dsize[0]), int(dsize[1])
-    M3 = P.affine_to_homography(M)  # raises ValueError for non (B,2,3), like conversions.py:375-376
-    m = P.inverse3x3(P.normalize_homography(M3, (H, W), (h_out, w_out)))
+    if not (M.dim() == 3 and tuple(M.shape[-2:]) == (2, 3)):  # conversions.py:375-376
+        raise ValueError(f"Input matrix must be a Bx2x3 tensor. Got {M.shape}")
+    m = P.sampling_matrix(M, (H, W), (h_out, w_out), affine=True)
     B_M = M.shape[0]
     if B_M != B and not (B_M == 1 and B > 1):
         raise RuntimeError(f"grid_sampler(): expected grid and input to have same batch size, but got input with sizes "

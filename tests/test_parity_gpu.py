@@ -290,3 +290,35 @@ def test_batch_shards_equal_whole():
     other = torch.rand_like(src)
     lin = K.warp_perspective(src + other, M, (H, W))
     torch.testing.assert_close(lin, whole + K.warp_perspective(other, M, (H, W)), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_fused_prelude_bit_identical(dt):
+    """kb200_warp_prelude vs the reference's torch op sequence on the same device, over batch sizes (torch picks
+    different GEMM kernels by size), image sizes and both matrix kinds."""
+    from kornia_b200.geometry import _prelude as P
+
+    g = torch.Generator().manual_seed(11)
+    bad = {}
+    for n in (2, 3, 4, 5, 7, 8, 16, 31, 64, 100, 256, 1000, 2048):
+        for (H, W, h, w) in ((1080, 1920, 1080, 1920), (720, 1280, 360, 640), (37, 53, 29, 41), (64, 64, 64, 64)):
+            M = torch.eye(3)[None].repeat(n, 1, 1) + 0.2 * torch.randn(n, 3, 3, generator=g)
+            M[:, 2, :2] *= 0.001
+            M = M.to(dt).to(DEV)
+            want = P.inverse3x3(P.normalize_homography(M, (H, W), (h, w)))
+            got = P.sampling_matrix(M, (H, W), (h, w), affine=False)
+            A = M[:, :2].contiguous()
+            want_a = P.inverse3x3(P.normalize_homography(P.affine_to_homography(A), (H, W), (h, w)))
+            got_a = P.sampling_matrix(A, (H, W), (h, w), affine=True)
+            nb = int((got != want).sum()) + int((got_a != want_a).sum())
+            if nb:
+                bad[(n, H, W)] = nb
+    assert not bad, bad
+
+
+def test_prelude_keeps_autograd_path():
+    M = (torch.eye(3, device=DEV)[None].repeat(4, 1, 1) + 0.01).requires_grad_()
+    src = torch.rand(4, 3, 32, 64, device=DEV, requires_grad=True)
+    out = K.warp_perspective(src, M, (32, 64))
+    gs, gm = torch.autograd.grad(out.sum(), [src, M])
+    assert gs.shape == src.shape and gm.shape == M.shape and float(gm.abs().sum()) > 0
