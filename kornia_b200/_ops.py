@@ -110,7 +110,7 @@ class WarpFunction(torch.autograd.Function):
             gm = torch.empty_like(m)
             nbytes = _lib.load().kb200_warp_backward_workspace_bytes(B, h, w, dt)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
-        with torch.cuda.device(src.device):
+        with torch.cuda.device(src.device), _Timed("warp_backward", src):
             _lib.call("kb200_warp_backward", _ptr(gout), _ptr(src), _ptr(m), _ptr(bx), _ptr(by),
                       _ptr(fill) if has_fill else None, _ptr(gsrc), _ptr(gm), _ptr(ws),
                       B, C, H, W, h, w, m.shape[0], projective, interp, pad, align, dt, _stream(src))

@@ -322,3 +322,35 @@ def test_prelude_keeps_autograd_path():
     out = K.warp_perspective(src, M, (32, 64))
     gs, gm = torch.autograd.grad(out.sum(), [src, M])
     assert gs.shape == src.shape and gm.shape == M.shape and float(gm.abs().sum()) > 0
+
+
+# ------------------------------------------------------------------ the tiled separable filter
+@pytest.mark.parametrize("border", ["constant", "reflect", "replicate"])
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13, 15, 17])
+def test_tiled_sepfilter_bit_identical_to_generic(k, border):
+    import os
+
+    g = torch.Generator().manual_seed(k)
+    for (B, C, H, W) in ((2, 3, 70, 200), (1, 1, 32, 128), (3, 2, 45, 132), (1, 3, 9 + k, 12 + 4 * (k // 4))):
+        x = torch.rand(B, C, H, W, generator=g).to(DEV)
+        kx = torch.randn(B, k, generator=g).to(DEV)
+        ky = torch.randn(1, k, generator=g).to(DEV)
+        a = K.filter2d_separable(x, kx, ky, border)
+        os.environ["KB200_DISABLE_TILED_FILTER"] = "1"
+        try:
+            b = K.filter2d_separable(x, kx, ky, border)
+        finally:
+            del os.environ["KB200_DISABLE_TILED_FILTER"]
+        assert torch.equal(a, b), (B, C, H, W, float((a - b).abs().max()))
+        want = R.filter2d_separable(x.cpu(), kx.cpu(), ky.cpu(), border)
+        torch.testing.assert_close(a.cpu(), want, rtol=1e-4, atol=1e-5)
+
+
+def test_gaussian_blur_1080p_vs_oracle():
+    """BASELINE.json configs[2] shape at reduced batch, against the CPU oracle (reference ops)."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 3, 1080, 1920, generator=g)
+    a = K.gaussian_blur2d(x.to(DEV), (11, 11), (2.0, 2.0)).cpu()
+    want = R.gaussian_blur2d(x, (11, 11), (2.0, 2.0))
+    assert rel_l2(a, want) < 1e-6, rel_l2(a, want)
+    torch.testing.assert_close(a, want, rtol=1e-4, atol=1e-5)
