@@ -30,23 +30,57 @@ def gaussian_blur2d(
     check_shape(input, ["B", "C", "H", "W"])
     _check_kernel_size(kernel_size, min_value=0)
 
+    sigma_key = None
     if isinstance(sigma, tuple):
-        sigma = torch.tensor([sigma], device=input.device, dtype=input.dtype)
+        # constant sigmas: validate on the host (same verdict as the reference's device-side
+        # `(sigma > 0).all()`, without its device->host sync) and reuse the taps across calls
+        sigma_key = tuple(float(v) for v in sigma)
+        if len(sigma_key) != 2:  # let the reference's shape check word the error
+            check_shape(torch.tensor([sigma_key]), ["B", "2"])
+        ok = all(v > 0 for v in sigma_key)
+        sigma_t = None
     else:
         check_is_tensor(sigma)
-        sigma = sigma.to(device=input.device, dtype=input.dtype)
-    check_shape(sigma, ["B", "2"])
-    if not torch.compiler.is_compiling():
-        ok = bool((sigma > 0).all())  # device->host sync, as in the reference (gaussian.py:107)
-        check(ok, "sigma must be positive" if ok else f"sigma must be positive, got {sigma}")
+        sigma_t = sigma.to(device=input.device, dtype=input.dtype)
+        check_shape(sigma_t, ["B", "2"])
+        ok = True
+        if not torch.compiler.is_compiling():
+            ok = bool((sigma_t > 0).all())  # device->host sync, as in the reference (gaussian.py:107)
+    if sigma_key is not None and not ok:
+        sigma_t = torch.tensor([sigma_key], device=input.device, dtype=input.dtype)
+    check(ok, "sigma must be positive" if ok else f"sigma must be positive, got {sigma_t}")
 
+    if sigma_key is not None:
+        kernels = _constant_taps(kernel_size, sigma_key, separable, input.device, input.dtype)
+    else:
+        kernels = _taps(kernel_size, sigma_t, separable)
+    if separable:
+        return filter2d_separable(input, kernels[0], kernels[1], border_type)
+    return filter2d(input, kernels[0], border_type)
+
+
+def _taps(kernel_size, sigma: torch.Tensor, separable: bool):
+    """(kernel_x, kernel_y) or (kernel2d,) built with the reference's torch ops (gaussian.py:111-117)."""
     if separable:
         ky, kx = _unpack_2d_ks(kernel_size)
         bs = sigma.shape[0]
-        kernel_x = get_gaussian_kernel1d(kx, sigma[:, 1].view(bs, 1))
-        kernel_y = get_gaussian_kernel1d(ky, sigma[:, 0].view(bs, 1))
-        return filter2d_separable(input, kernel_x, kernel_y, border_type)
-    return filter2d(input, get_gaussian_kernel2d(kernel_size, sigma), border_type)
+        return (get_gaussian_kernel1d(kx, sigma[:, 1].view(bs, 1)), get_gaussian_kernel1d(ky, sigma[:, 0].view(bs, 1)))
+    return (get_gaussian_kernel2d(kernel_size, sigma),)
+
+
+_TAPS_CACHE: dict = {}
+
+
+def _constant_taps(kernel_size, sigma_key, separable, device, dtype):
+    ks = kernel_size if isinstance(kernel_size, int) else tuple(kernel_size)
+    key = (ks, sigma_key, bool(separable), str(device), dtype)
+    hit = _TAPS_CACHE.get(key)
+    if hit is None:
+        if len(_TAPS_CACHE) >= 256:
+            _TAPS_CACHE.clear()
+        with torch.no_grad():
+            hit = _TAPS_CACHE[key] = _taps(kernel_size, torch.tensor([sigma_key], device=device, dtype=dtype), separable)
+    return hit
 
 
 class GaussianBlur2d(nn.Module):
