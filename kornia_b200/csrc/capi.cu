@@ -7,6 +7,7 @@
 #include "prelude.cuh"
 #include "warp_generic.cuh"
 #include "warp_tma.cuh"
+#include "warp_bwd_tma.cuh"
 #include "sepfilter_tiled.cuh"
 
 namespace kb200 {
@@ -182,7 +183,9 @@ int kb200_warp_forward(const void* src, const void* m, const void* bx, const voi
 
 size_t kb200_warp_backward_workspace_bytes(int B, int h, int w, int dtype) {
   const size_t nblk = (size_t)ceil_div(w, GEN_BX) * ceil_div(h, GEN_BY);
-  return (size_t)B * nblk * 9 * (dtype == KB200_F64 ? 8 : 4);
+  const size_t generic = (size_t)B * nblk * 9 * (dtype == KB200_F64 ? 8 : 4);
+  const size_t tiled = dtype == KB200_F32 ? bwd_tma_workspace_bytes(B, h) : 0;
+  return generic > tiled ? generic : tiled;
 }
 
 template <typename T>
@@ -211,9 +214,13 @@ int kb200_warp_backward(const void* gout, const void* src, const void* m, const 
   KB_CHECK_ARG(!gm || workspace, "gm requested without workspace");
   KB_CHECK_ARG(pad != KB200_FILL || fill, "pad=fill needs a fill vector");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == KB200_F32)
+  if (dtype == KB200_F32) {
+    rc = warp_tma_backward((const float*)gout, (const float*)src, (const float*)m, (const float*)bx, (const float*)by, (float*)gsrc,
+                           (float*)gm, workspace, B, C, H, W, h, w, Bm, projective, interp, pad, align_corners, st);
+    if (rc != KB200_EUNSUPPORTED) return rc;
     return warp_backward_t<float>(gout, src, m, bx, by, fill, gsrc, gm, workspace, B, C, H, W, h, w, Bm, projective, interp,
                                   pad, align_corners, st);
+  }
   return warp_backward_t<double>(gout, src, m, bx, by, fill, gsrc, gm, workspace, B, C, H, W, h, w, Bm, projective, interp,
                                  pad, align_corners, st);
 }

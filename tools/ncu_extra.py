@@ -10,7 +10,7 @@ if what == "blur":
     for _ in range(3):
         y = K.gaussian_blur2d(x, (11, 11), (2.0, 2.0))
 else:
-    B, H, W = 8, 720, 1280
+    B, H, W = 32, 720, 1280
     src = torch.rand(B, 3, H, W, device="cuda", requires_grad=True)
     g = torch.Generator().manual_seed(7)
     quad = torch.tensor([[0.0, 0.0], [W - 1.0, 0.0], [W - 1.0, H - 1.0], [0.0, H - 1.0]]).expand(B, 4, 2)
