@@ -15,7 +15,6 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-Xcompiler", "-fPIC",
-    "-shared",
 ]
 
 
@@ -32,17 +31,32 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile kornia_b200/csrc/*.cu into kornia_b200/_C/libkornia_b200.so; returns the path."""
+    """Compile kornia_b200/csrc/*.cu (one object per file, in parallel) and link
+    kornia_b200/_C/libkornia_b200.so; returns the path."""
     if not force and not _stale():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("kornia_b200.build: nvcc not found; cannot build the CUDA library")
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + _sources()
+    obj_dir = os.path.join(OUT_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        if verbose:
+            print(proc.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, _sources()))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     return OUT

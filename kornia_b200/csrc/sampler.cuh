@@ -96,17 +96,20 @@ __device__ __forceinline__ T pad_coord_grad(T c, int size, bool align, T* mult) 
   return guard_index(c);
 }
 
-// cubic convolution weights for the four taps at offsets -1, 0, 1, 2 (A = -0.75)
+// cubic convolution weights for the four taps at offsets -1, 0, 1, 2 (A = -0.75), Horner form with the
+// fused multiply-adds a -fmad=true build of UpSample.h:398-423 produces (explicit, so every kernel of
+// this library rounds them identically)
 template <typename T>
 __device__ __forceinline__ void cubic_weights(T t, T w[4]) {
+  using R = RN<T>;
   const T A = T(-0.75);
-  const T x0 = t + T(1);
-  w[0] = ((A * x0 - T(5) * A) * x0 + T(8) * A) * x0 - T(4) * A;
-  w[1] = ((A + T(2)) * t - (A + T(3))) * t * t + T(1);
-  const T u = T(1) - t;
-  w[2] = ((A + T(2)) * u - (A + T(3))) * u * u + T(1);
-  const T x3 = u + T(1);
-  w[3] = ((A * x3 - T(5) * A) * x3 + T(8) * A) * x3 - T(4) * A;
+  const T x0 = R::add(t, T(1));
+  w[0] = R::fma(R::fma(R::fma(A, x0, T(3.75)), x0, T(-6)), x0, T(3));          // ((A x - 5A) x + 8A) x - 4A
+  w[1] = R::fma(R::mul(R::fma(T(1.25), t, T(-2.25)), t), t, T(1));             // ((A+2) x - (A+3)) x x + 1
+  const T u = R::sub(T(1), t);
+  w[2] = R::fma(R::mul(R::fma(T(1.25), u, T(-2.25)), u), u, T(1));
+  const T x3 = R::add(u, T(1));
+  w[3] = R::fma(R::fma(R::fma(A, x3, T(3.75)), x3, T(-6)), x3, T(3));
 }
 
 // d(weights)/dt (GridSampler.h get_cubic_coefficients_grad)
@@ -126,6 +129,116 @@ __device__ __forceinline__ void cubic_weights_grad(T t, T w[4]) {
 __device__ __forceinline__ bool in_bounds(int y, int x, int H, int W) {
   return (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
 }
+
+// Exact per-pixel sampler on a global-memory plane: everything about one output pixel that does not
+// depend on the channel (tap offsets, bounds flags, weights, fill coverage) is prepared once, then
+// `sample(plane)` is called per channel.  Shared by the generic kernel and by the careful path of the
+// tiled kernel, so the two are the same arithmetic by construction.  PAD == KB200_FILL samples with
+// zeros padding and exposes 1 - coverage (imgwarp.py:308-320).
+template <typename T, int INTERP, int PAD>
+struct PixelSampler {
+  static constexpr int SPAD = (PAD == KB200_FILL) ? KB200_ZEROS : PAD;
+  static constexpr int NT = (INTERP == KB200_BICUBIC) ? 4 : 1;
+  int o;            // bilinear / nearest: offset of the first tap
+  int W;
+  bool ok[4];       // bilinear: nw, ne, sw, se ; nearest: ok[0]
+  T w[4];           // bilinear weights
+  int xo[NT], yo[NT];
+  bool xok[NT], yok[NT];
+  T cx[NT], cy[NT];
+  T inv_cover;
+
+  __device__ __forceinline__ void prepare(T ix, T iy, int H, int W_, bool align) {
+    using R = RN<T>;
+    W = W_;
+    inv_cover = T(0);
+    if (INTERP == KB200_BILINEAR) {
+      ix = pad_coord<T, SPAD>(ix, W, align);
+      iy = pad_coord<T, SPAD>(iy, H, align);
+      const T x0f = R::floor(ix), y0f = R::floor(iy);
+      const T x1f = R::add(x0f, T(1)), y1f = R::add(y0f, T(1));
+      const T wx1 = R::sub(x1f, ix), wx0 = R::sub(ix, x0f);
+      const T wy1 = R::sub(y1f, iy), wy0 = R::sub(iy, y0f);
+      w[0] = R::mul(wx1, wy1); w[1] = R::mul(wx0, wy1); w[2] = R::mul(wx1, wy0); w[3] = R::mul(wx0, wy0);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      ok[0] = in_bounds(y0, x0, H, W); ok[1] = in_bounds(y0, x0 + 1, H, W);
+      ok[2] = in_bounds(y0 + 1, x0, H, W); ok[3] = in_bounds(y0 + 1, x0 + 1, H, W);
+      o = y0 * W + x0;
+      if (PAD == KB200_FILL) {
+        T cover = T(0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (ok[k]) cover = R::add(cover, w[k]);
+        inv_cover = R::sub(T(1), cover);
+      }
+    } else if (INTERP == KB200_NEAREST) {
+      ix = pad_coord<T, SPAD>(ix, W, align);
+      iy = pad_coord<T, SPAD>(iy, H, align);
+      const int xn = (int)R::rint(ix), yn = (int)R::rint(iy);
+      ok[0] = in_bounds(yn, xn, H, W);
+      o = yn * W + xn;
+      if (PAD == KB200_FILL) inv_cover = ok[0] ? T(0) : T(1);
+    } else {  // bicubic: coordinates stay un-padded, every tap is padded on its own
+      const T fx = R::floor(ix), fy = R::floor(iy);
+      cubic_weights<T>(R::sub(ix, fx), cx);
+      cubic_weights<T>(R::sub(iy, fy), cy);
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        const int xi = (int)pad_coord<T, SPAD>(R::add(R::sub(fx, T(1)), T(i)), W, align);
+        const int yi = (int)pad_coord<T, SPAD>(R::add(R::sub(fy, T(1)), T(i)), H, align);
+        xok[i] = (unsigned)xi < (unsigned)W;
+        yok[i] = (unsigned)yi < (unsigned)H;
+        xo[i] = xi;
+        yo[i] = yi * W;
+      }
+      if (PAD == KB200_FILL) {
+        T cover = T(0);
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          T r = T(0);
+#pragma unroll
+          for (int j = 0; j < NT; ++j) r = R::fma((yok[i] && xok[j]) ? T(1) : T(0), cx[j], r);
+          cover = R::fma(r, cy[i], cover);
+        }
+        inv_cover = R::sub(T(1), cover);
+      }
+    }
+  }
+
+  __device__ __forceinline__ T sample(const T* __restrict__ s) const {
+    using R = RN<T>;
+    if (INTERP == KB200_BILINEAR) {
+      T acc = T(0);
+      if (ok[0]) acc = R::fma(ldg(s + o), w[0], acc);
+      if (ok[1]) acc = R::fma(ldg(s + o + 1), w[1], acc);
+      if (ok[2]) acc = R::fma(ldg(s + o + W), w[2], acc);
+      if (ok[3]) acc = R::fma(ldg(s + o + W + 1), w[3], acc);
+      return acc;
+    } else if (INTERP == KB200_NEAREST) {
+      return ok[0] ? ldg(s + o) : T(0);
+    } else {
+      T acc = T(0);
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        T r = T(0);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const T v = (yok[i] && xok[j]) ? ldg(s + yo[i] + xo[j]) : T(0);
+          r = R::fma(v, cx[j], r);
+        }
+        acc = R::fma(r, cy[i], acc);
+      }
+      return acc;
+    }
+  }
+
+  // value written for a channel: sample (+ (1 - coverage) * fill for PAD == KB200_FILL)
+  __device__ __forceinline__ T finish(T v, T fill) const {
+    using R = RN<T>;
+    if (PAD == KB200_FILL) return R::add(v, R::mul(inv_cover, fill));
+    return v;
+  }
+};
 
 // Per-sample 3x3 matrix held in registers; the map of A.3 with the reference's association order.
 template <typename T>

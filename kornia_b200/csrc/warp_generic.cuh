@@ -84,8 +84,6 @@ __device__ __forceinline__ Coord<T, KIND> coord_of(const WarpParams<T>& p, const
 // ------------------------------------------------------------------------------------------
 template <typename T, int INTERP, int PAD, int KIND>
 __global__ void __launch_bounds__(GEN_BX* GEN_BY) warp_fwd_generic(const WarpParams<T> p) {
-  using R = RN<T>;
-  constexpr int SPAD = (PAD == KB200_FILL) ? KB200_ZEROS : PAD;  // fill samples with zeros padding
   const int x = blockIdx.x * GEN_BX + threadIdx.x;
   const int y = blockIdx.y * GEN_BY + threadIdx.y;
   const int b = blockIdx.z;
@@ -100,95 +98,11 @@ __global__ void __launch_bounds__(GEN_BX* GEN_BY) warp_fwd_generic(const WarpPar
   const T* sp = p.src + (size_t)b * p.C * splane;
   T* op = p.out + (size_t)b * p.C * oplane + (size_t)y * p.w + x;
 
-  T ix = unnormalize(c.gx, W, align);
-  T iy = unnormalize(c.gy, H, align);
-
-  if (INTERP == KB200_BILINEAR) {
-    ix = pad_coord<T, SPAD>(ix, W, align);
-    iy = pad_coord<T, SPAD>(iy, H, align);
-    const T x0f = R::floor(ix), y0f = R::floor(iy);
-    const T x1f = R::add(x0f, T(1)), y1f = R::add(y0f, T(1));
-    const T wx1 = R::sub(x1f, ix), wx0 = R::sub(ix, x0f);
-    const T wy1 = R::sub(y1f, iy), wy0 = R::sub(iy, y0f);
-    const T w_nw = R::mul(wx1, wy1), w_ne = R::mul(wx0, wy1), w_sw = R::mul(wx1, wy0), w_se = R::mul(wx0, wy0);
-    const int x0 = (int)x0f, y0 = (int)y0f;
-    const bool ok_nw = in_bounds(y0, x0, H, W), ok_ne = in_bounds(y0, x0 + 1, H, W);
-    const bool ok_sw = in_bounds(y0 + 1, x0, H, W), ok_se = in_bounds(y0 + 1, x0 + 1, H, W);
-    const int o_nw = y0 * W + x0;
-    T inv_cover = T(0);
-    if (PAD == KB200_FILL) {
-      T cover = T(0);
-      if (ok_nw) cover = R::add(cover, w_nw);
-      if (ok_ne) cover = R::add(cover, w_ne);
-      if (ok_sw) cover = R::add(cover, w_sw);
-      if (ok_se) cover = R::add(cover, w_se);
-      inv_cover = R::sub(T(1), cover);
-    }
-    for (int ch = 0; ch < p.C; ++ch) {
-      const T* s = sp + ch * splane;
-      T acc = T(0);
-      if (ok_nw) acc = R::fma(ldg(s + o_nw), w_nw, acc);
-      if (ok_ne) acc = R::fma(ldg(s + o_nw + 1), w_ne, acc);
-      if (ok_sw) acc = R::fma(ldg(s + o_nw + W), w_sw, acc);
-      if (ok_se) acc = R::fma(ldg(s + o_nw + W + 1), w_se, acc);
-      if (PAD == KB200_FILL) acc = R::add(acc, R::mul(inv_cover, ldg(p.fill + ch)));
-      st_stream(op + ch * oplane, acc);
-    }
-  } else if (INTERP == KB200_NEAREST) {
-    ix = pad_coord<T, SPAD>(ix, W, align);
-    iy = pad_coord<T, SPAD>(iy, H, align);
-    const int xn = (int)R::rint(ix), yn = (int)R::rint(iy);
-    const bool ok = in_bounds(yn, xn, H, W);
-    const int o = yn * W + xn;
-    for (int ch = 0; ch < p.C; ++ch) {
-      T v = ok ? ldg(sp + ch * splane + o) : T(0);
-      if (PAD == KB200_FILL) v = R::add(v, R::mul(ok ? T(0) : T(1), ldg(p.fill + ch)));
-      st_stream(op + ch * oplane, v);
-    }
-  } else {  // bicubic: coordinates stay un-padded, every tap is padded on its own
-    const T fx = R::floor(ix), fy = R::floor(iy);
-    T cx[4], cy[4];
-    cubic_weights<T>(R::sub(ix, fx), cx);
-    cubic_weights<T>(R::sub(iy, fy), cy);
-    int xo[4], yo[4];
-    bool xok[4], yok[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int xi = (int)pad_coord<T, SPAD>(R::add(R::sub(fx, T(1)), T(i)), W, align);
-      const int yi = (int)pad_coord<T, SPAD>(R::add(R::sub(fy, T(1)), T(i)), H, align);
-      xok[i] = (unsigned)xi < (unsigned)W;
-      yok[i] = (unsigned)yi < (unsigned)H;
-      xo[i] = xi;
-      yo[i] = yi * W;
-    }
-    T inv_cover = T(0);
-    if (PAD == KB200_FILL) {
-      T cover = T(0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        T r = T(0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r = R::fma((yok[i] && xok[j]) ? T(1) : T(0), cx[j], r);
-        cover = R::fma(r, cy[i], cover);
-      }
-      inv_cover = R::sub(T(1), cover);
-    }
-    for (int ch = 0; ch < p.C; ++ch) {
-      const T* s = sp + ch * splane;
-      T acc = T(0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        T r = T(0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const T v = (yok[i] && xok[j]) ? ldg(s + yo[i] + xo[j]) : T(0);
-          r = R::fma(v, cx[j], r);
-        }
-        acc = R::fma(r, cy[i], acc);
-      }
-      if (PAD == KB200_FILL) acc = R::add(acc, R::mul(inv_cover, ldg(p.fill + ch)));
-      st_stream(op + ch * oplane, acc);
-    }
+  PixelSampler<T, INTERP, PAD> S;
+  S.prepare(unnormalize(c.gx, W, align), unnormalize(c.gy, H, align), H, W, align);
+  for (int ch = 0; ch < p.C; ++ch) {
+    const T v = S.sample(sp + ch * splane);
+    st_stream(op + ch * oplane, S.finish(v, PAD == KB200_FILL ? ldg(p.fill + ch) : T(0)));
   }
 }
 

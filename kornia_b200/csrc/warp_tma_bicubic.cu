@@ -1,0 +1,6 @@
+// kornia_b200 -- instantiations of the TMA-tiled warp forward kernel, bicubic interpolation.
+#include "warp_tma_host.cuh"
+
+namespace kb200 {
+int warp_tma_forward_bicubic(const TmaFwdArgs& a, cudaStream_t st) { return warp_tma_forward_impl<KB200_BICUBIC>(a, st); }
+}  // namespace kb200

@@ -210,25 +210,39 @@ def _wild_matrices(H, W):
     return torch.tensor(mats, dtype=torch.float32)
 
 
-@pytest.mark.parametrize("pad", ["zeros", "border", "reflection"])
+_TILED_CASES = ([("bilinear", pad, C) for pad in ("zeros", "border", "reflection") for C in (1, 3, 4)] +
+                [("bilinear", "fill", 3)] +
+                [(mode, pad, 3) for mode in ("nearest", "bicubic") for pad in ("zeros", "border", "reflection", "fill")] +
+                [("bicubic", "zeros", 1), ("nearest", "border", 1)])
+
+
+@pytest.mark.parametrize("mode,pad,C", _TILED_CASES)
 @pytest.mark.parametrize("ac", [True, False])
-@pytest.mark.parametrize("C", [1, 3, 4])
-def test_tiled_kernel_bit_identical_to_generic(pad, ac, C):
+def test_tiled_kernel_bit_identical_to_generic(mode, pad, C, ac):
+    """Every mode the tiled kernel serves must reproduce the generic kernel exactly (the staged tile is only a
+    cache): rotations, zoom, strong perspective, a horizon inside the image, everything out of view."""
     H, W = 216, 384
     M = torch.cat([_wild_matrices(H, W), _bench_homographies(6, H, W, 5, sigma=4.0)]).to(DEV)
     src = torch.rand(M.shape[0], C, H, W, device=DEV)
+    fv = torch.tensor([0.2, 0.5, 0.8], device=DEV) if pad == "fill" else None
     from kornia_b200 import _lib
 
+    def same(a, b):
+        if mode == "nearest":  # identical arithmetic; NaN-safe comparison
+            return torch.equal(a.nan_to_num(nan=-7.0), b.nan_to_num(nan=-7.0))
+        return torch.equal(a.nan_to_num(nan=-7.0), b.nan_to_num(nan=-7.0))
+
     for dsize in ((H, W), (150, 333)):
-        a = K.warp_perspective(src, M, dsize, padding_mode=pad, align_corners=ac)
+        a = K.warp_perspective(src, M, dsize, mode=mode, padding_mode=pad, align_corners=ac, fill_value=fv)
         assert _lib.last_warp_variant() == "tma_tile"
-        b = _generic(lambda: K.warp_perspective(src, M, dsize, padding_mode=pad, align_corners=ac))
-        assert torch.equal(a.nan_to_num(nan=-7.0), b.nan_to_num(nan=-7.0)), float((a - b).abs().nan_to_num().max())
+        b = _generic(lambda: K.warp_perspective(src, M, dsize, mode=mode, padding_mode=pad, align_corners=ac, fill_value=fv))
+        assert same(a, b), (dsize, float((a - b).abs().nan_to_num().max()))
         A = M[:, :2, :].contiguous()
-        a = K.warp_affine(src, A, dsize, padding_mode=pad, align_corners=ac)
+        fa = fv if C == 3 or fv is None else fv[:C]
+        a = K.warp_affine(src, A, dsize, mode=mode, padding_mode=pad, align_corners=ac, fill_value=fa)
         assert _lib.last_warp_variant() == "tma_tile"
-        b = _generic(lambda: K.warp_affine(src, A, dsize, padding_mode=pad, align_corners=ac))
-        assert torch.equal(a, b)
+        b = _generic(lambda: K.warp_affine(src, A, dsize, mode=mode, padding_mode=pad, align_corners=ac, fill_value=fa))
+        assert same(a, b), ("affine", dsize, float((a - b).abs().nan_to_num().max()))
 
 
 def test_fast_division_is_ieee():

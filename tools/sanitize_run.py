@@ -1,0 +1,24 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck): tiled forward (3 interpolations),
+tiled backward, tiled separable filter, at sizes with several tiles per CTA and partial edge tiles."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import kornia_b200 as K
+dev = "cuda"
+g = torch.Generator().manual_seed(0)
+B, C, H, W = 3, 3, 100, 192
+src = torch.rand(B, C, H, W, generator=g).to(dev)
+M = (torch.eye(3)[None].repeat(B, 1, 1) + 0.01 * torch.randn(B, 3, 3, generator=g))
+M[:, 2, :2] *= 0.01
+M = M.to(dev)
+for mode in ("bilinear", "nearest", "bicubic"):
+    for pad in ("zeros", "fill"):
+        K.warp_perspective(src, M, (90, 200), mode=mode, padding_mode=pad, fill_value=torch.tensor([0.1, 0.2, 0.3], device=dev))
+s = src.clone().requires_grad_(True)
+m = M.clone().requires_grad_(True)
+out = K.warp_perspective(s, m, (H, W))
+torch.autograd.grad(out.sum(), [s, m])
+K.gaussian_blur2d(src, (11, 11), (2.0, 2.0))
+K.gaussian_blur2d(src, (5, 5), (1.0, 1.0), "replicate")
+torch.cuda.synchronize()
+print("sanitize workload done")
