@@ -59,4 +59,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    shutil.rmtree(obj_dir, ignore_errors=True)  # only the .so travels to the GPU box
     return OUT
