@@ -73,6 +73,10 @@ int kb200_warp_forward(const void* src, const void* m, const void* bx, const voi
 int kb200_warp_prelude(const void* M, void* m_out, int B, int rows, int H, int W, int h, int w, int dtype,
                        int variant, void* stream);
 
+/* Backward of kb200_warp_prelude: gM (B,rows,3) = dL/dM given m (B,3,3) = the prelude's output and gm = dL/dm. */
+int kb200_warp_prelude_backward(const void* m, const void* gm, void* gM, int B, int rows, int H, int W, int h, int w,
+                                int dtype, void* stream);
+
 /* Backward of the above w.r.t. src and m (replaces grid_sampler_2d_backward + the autograd of
  * imgwarp.py:165-170).
  *   gout (B,C,h,w) upstream gradient

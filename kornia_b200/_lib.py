@@ -32,6 +32,7 @@ SIGNATURES = {
     "kb200_last_warp_variant": (ctypes.c_char_p, []),
     "kb200_warp_forward": (_i, [_vp] * 6 + [_i] * 12 + [_vp]),
     "kb200_warp_prelude": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),
+    "kb200_warp_prelude_backward": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "kb200_warp_backward_workspace_bytes": (_sz, [_i] * 4),
     "kb200_warp_backward": (_i, [_vp] * 9 + [_i] * 12 + [_vp]),
     "kb200_remap_forward": (_i, [_vp] * 4 + [_i] * 12 + [_vp]),
@@ -73,6 +74,18 @@ def load() -> ctypes.CDLL:
     return _lib
 
 
+def _opaque(fn):
+    """Keep torch.compile / dynamo out of the ctypes layer: the ops become opaque graph breaks (the
+    reference's tracing branches are out of scope; north_star: no multi-backend dispatch)."""
+    try:
+        import torch
+
+        return torch.compiler.disable(fn)
+    except Exception:  # very old torch
+        return fn
+
+
+@_opaque
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and turn a non-zero status into ``RuntimeError``."""
     lib = load()

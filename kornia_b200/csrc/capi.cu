@@ -449,6 +449,23 @@ int kb200_warp_prelude(const void* M, void* m_out, int B, int rows, int H, int W
   return post_launch("warp_prelude");
 }
 
+int kb200_warp_prelude_backward(const void* m, const void* gm, void* gM, int B, int rows, int H, int W, int h, int w, int dtype,
+                                void* stream) {
+  KB_CHECK_ARG(m && gm && gM && B > 0, "bad arguments");
+  KB_CHECK_ARG(rows == 2 || rows == 3, "rows must be 2 (affine) or 3 (projective), got %d", rows);
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  const float sx_s = (float)(2.0 / (W == 1 ? 1e-14 : (double)W - 1.0)), sy_s = (float)(2.0 / (H == 1 ? 1e-14 : (double)H - 1.0));
+  const float sx_d = (float)(2.0 / (w == 1 ? 1e-14 : (double)w - 1.0)), sy_d = (float)(2.0 / (h == 1 ? 1e-14 : (double)h - 1.0));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(B, 128);
+  if (dtype == KB200_F32)
+    warp_prelude_backward_kernel<float><<<grid, 128, 0, st>>>((const float*)m, (const float*)gm, (float*)gM, B, rows, sx_s, sy_s, sx_d, sy_d);
+  else
+    warp_prelude_backward_kernel<double><<<grid, 128, 0, st>>>((const double*)m, (const double*)gm, (double*)gM, B, rows, sx_s, sy_s, sx_d,
+                                                               sy_d);
+  return post_launch("warp_prelude_backward");
+}
+
 // ------------------------------------------------------------------------------------------
 // diagnostics
 // ------------------------------------------------------------------------------------------

@@ -82,4 +82,41 @@ __global__ void warp_prelude_kernel(const T* __restrict__ M, T* __restrict__ out
   for (int i = 0; i < 9; ++i) out[(size_t)b * 9 + i] = m[i];
 }
 
+// Backward of the prelude: given m = inverse(Nd @ M3 @ inverse(Ns)) and gm = dL/dm, returns dL/dM3 (rows x 3).
+//   Mn = Nd M3 Nsi,  m = Mn^-1   =>   dL/dMn = -m^T gm m^T ,   dL/dM3 = Nd^T dL/dMn Nsi^T
+// Plain arithmetic (double accumulation): gradients carry no bit-exactness contract.
+template <typename T>
+__global__ void warp_prelude_backward_kernel(const T* __restrict__ m, const T* __restrict__ gm, T* __restrict__ gM, int B, int rows,
+                                             float sx_s, float sy_s, float sx_d, float sy_d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double mm[9], g[9], t[9], gn[9];
+  for (int i = 0; i < 9; ++i) {
+    mm[i] = (double)m[(size_t)b * 9 + i];
+    g[i] = (double)gm[(size_t)b * 9 + i];
+  }
+  // t = m^T g
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) t[i * 3 + j] = mm[0 * 3 + i] * g[0 * 3 + j] + mm[1 * 3 + i] * g[1 * 3 + j] + mm[2 * 3 + i] * g[2 * 3 + j];
+  // gn = -(t m^T)
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) gn[i * 3 + j] = -(t[i * 3 + 0] * mm[j * 3 + 0] + t[i * 3 + 1] * mm[j * 3 + 1] + t[i * 3 + 2] * mm[j * 3 + 2]);
+  // Nd = [[a,0,-1],[0,c,-1],[0,0,1]] ; Nsi = inverse of [[p,0,-1],[0,q,-1],[0,0,1]] = [[1/p,0,1/p],[0,1/q,1/q],[0,0,1]]
+  const double a = (double)(T)sx_d, c = (double)(T)sy_d, ip = 1.0 / (double)(T)sx_s, iq = 1.0 / (double)(T)sy_s;
+  // u = Nd^T gn : rows (a*gn0, c*gn1, -gn0 - gn1 + gn2)
+  double u[9];
+  for (int j = 0; j < 3; ++j) {
+    u[0 * 3 + j] = a * gn[0 * 3 + j];
+    u[1 * 3 + j] = c * gn[1 * 3 + j];
+    u[2 * 3 + j] = -gn[0 * 3 + j] - gn[1 * 3 + j] + gn[2 * 3 + j];
+  }
+  // gM = u Nsi^T : column k of Nsi^T is row k of Nsi
+  for (int i = 0; i < rows; ++i) {
+    const double u0 = u[i * 3], u1 = u[i * 3 + 1], u2 = u[i * 3 + 2];
+    gM[((size_t)b * rows + i) * 3 + 0] = (T)(u0 * ip + u2 * ip);
+    gM[((size_t)b * rows + i) * 3 + 1] = (T)(u1 * iq + u2 * iq);
+    gM[((size_t)b * rows + i) * 3 + 2] = (T)u2;
+  }
+}
+
 }  // namespace kb200

@@ -46,6 +46,7 @@ def _border_code(border_type: str, x: torch.Tensor, kh: int, kw: int, same: bool
     return code
 
 
+@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def filter2d(
     input: torch.Tensor,
     kernel: torch.Tensor,
@@ -79,6 +80,7 @@ def filter2d(
     return Filter2dFunction.apply(input, taps, _border_code(border_type, input, kh, kw, same), same)
 
 
+@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def filter2d_separable(
     input: torch.Tensor,
     kernel_x: torch.Tensor,

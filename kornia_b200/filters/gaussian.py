@@ -12,6 +12,7 @@ from .kernels import _check_kernel_size, _unpack_2d_ks, get_gaussian_kernel1d, g
 __all__ = ["gaussian_blur2d", "GaussianBlur2d"]
 
 
+@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def gaussian_blur2d(
     input: torch.Tensor,
     kernel_size: tuple[int, int] | int,

@@ -92,24 +92,49 @@ FUSED_VARIANT = 4       # the contraction orders that reproduce torch's CUDA ker
 FUSED_MIN_BATCH = 2     # below this torch's bmm takes a different (gemv-like) path; keep the torch ops there
 
 
+class _FusedPrelude(torch.autograd.Function):
+    """kb200_warp_prelude forward (bit-identical to the torch op sequence) + its one-launch backward."""
+
+    @staticmethod
+    def forward(ctx, M, src_hw, dst_hw, affine):
+        from .. import _lib, _ops
+
+        Mc = M.contiguous()
+        out = torch.empty((Mc.shape[0], 3, 3), device=M.device, dtype=M.dtype)
+        dt = 0 if M.dtype == torch.float32 else 1
+        with torch.cuda.device(M.device):
+            _lib.call("kb200_warp_prelude", Mc.data_ptr(), out.data_ptr(), Mc.shape[0], 2 if affine else 3, int(src_hw[0]), int(src_hw[1]),
+                      int(dst_hw[0]), int(dst_hw[1]), dt, FUSED_VARIANT, torch.cuda.current_stream(M.device).cuda_stream)
+        _ops._bump()
+        ctx.save_for_backward(out)
+        ctx.cfg = (tuple(int(v) for v in src_hw), tuple(int(v) for v in dst_hw), bool(affine), dt)
+        return out
+
+    @staticmethod
+    def backward(ctx, gm):
+        from .. import _lib, _ops
+
+        (m,) = ctx.saved_tensors
+        src_hw, dst_hw, affine, dt = ctx.cfg
+        rows = 2 if affine else 3
+        gm = gm.contiguous()
+        gM = torch.empty((m.shape[0], rows, 3), device=m.device, dtype=m.dtype)
+        with torch.cuda.device(m.device):
+            _lib.call("kb200_warp_prelude_backward", m.data_ptr(), gm.data_ptr(), gM.data_ptr(), m.shape[0], rows, src_hw[0], src_hw[1],
+                      dst_hw[0], dst_hw[1], dt, torch.cuda.current_stream(m.device).cuda_stream)
+        _ops._bump()
+        return gM, None, None, None
+
+
 def sampling_matrix(M: torch.Tensor, src_hw, dst_hw, affine: bool) -> torch.Tensor:
     """inverse(normalize_homography(M3)) -- the (B,3,3) dst-normalised -> src-normalised map the kernels
-    consume.  One CUDA launch when M is a plain CUDA fp32/fp64 tensor without grad; the reference's torch
-    op sequence (differentiable, same numbers) otherwise, or when KORNIA_B200_TORCH_PRELUDE=1."""
+    consume.  One CUDA launch (and one more for its backward) when M is a CUDA fp32/fp64 tensor with batch >= 2;
+    the reference's torch op sequence otherwise, under double backward, or when KORNIA_B200_TORCH_PRELUDE=1."""
     import os
 
-    fused_ok = (M.is_cuda and M.dtype in (torch.float32, torch.float64) and not (M.requires_grad and torch.is_grad_enabled())
-                and M.shape[0] >= FUSED_MIN_BATCH and os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") != "1")
+    fused_ok = (M.is_cuda and M.dtype in (torch.float32, torch.float64) and M.shape[0] >= FUSED_MIN_BATCH
+                and os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") != "1")
     if not fused_ok:
         M3 = affine_to_homography(M) if affine else M
         return inverse3x3(normalize_homography(M3, src_hw, dst_hw))
-    from .. import _lib, _ops
-
-    Mc = M.detach().contiguous()
-    out = torch.empty((Mc.shape[0], 3, 3), device=M.device, dtype=M.dtype)
-    with torch.cuda.device(M.device):
-        _lib.call("kb200_warp_prelude", Mc.data_ptr(), out.data_ptr(), Mc.shape[0], 2 if affine else 3, int(src_hw[0]), int(src_hw[1]),
-                  int(dst_hw[0]), int(dst_hw[1]), 0 if M.dtype == torch.float32 else 1, FUSED_VARIANT,
-                  torch.cuda.current_stream(M.device).cuda_stream)
-    _ops._bump()
-    return out
+    return _FusedPrelude.apply(M, src_hw, dst_hw, affine)

@@ -31,6 +31,7 @@ def _mode_codes(mode: str, padding_mode: str, allow_fill: bool):
     return _lib.INTERP[mode], _lib.PADDING[padding_mode]
 
 
+@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def warp_perspective(
     src: torch.Tensor,
     M: torch.Tensor,
@@ -80,6 +81,7 @@ def warp_perspective(
     return WarpFunction.apply(src, m, bx, by, fill, h_out, w_out, True, interp, pad, bool(align_corners))
 
 
+@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def warp_affine(
     src: torch.Tensor,
     M: torch.Tensor,
@@ -128,6 +130,7 @@ def warp_affine(
     return WarpFunction.apply(src, m, bx, by, fill, h_out, w_out, False, interp, pad, bool(align_corners))
 
 
+@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def remap(
     image: torch.Tensor,
     map_x: torch.Tensor,
