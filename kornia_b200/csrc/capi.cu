@@ -9,6 +9,7 @@
 #include "warp_tma.cuh"
 #include "warp_bwd_tma.cuh"
 #include "sepfilter_tiled.cuh"
+#include "filter2d_tiled.cuh"
 
 namespace kb200 {
 
@@ -332,8 +333,12 @@ int kb200_filter2d_forward(const void* x, const void* kernel, void* out, int B, 
   KB_CHECK_ARG(out, "null out");
   KB_CHECK_ARG((long long)B * C <= MAX_Z, "B*C = %lld planes exceed the %d-plane launch limit", (long long)B * C, MAX_Z);
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == KB200_F32 ? filter2d_forward_t<float>(x, kernel, out, B, C, H, W, Bk, kh, kw, border, same, st)
-                            : filter2d_forward_t<double>(x, kernel, out, B, C, H, W, Bk, kh, kw, border, same, st);
+  if (dtype == KB200_F32) {
+    rc = filter2d_tiled_forward((const float*)x, (const float*)kernel, (float*)out, B, C, H, W, Bk, kh, kw, border, same, st);
+    if (rc != KB200_EUNSUPPORTED) return rc;
+    return filter2d_forward_t<float>(x, kernel, out, B, C, H, W, Bk, kh, kw, border, same, st);
+  }
+  return filter2d_forward_t<double>(x, kernel, out, B, C, H, W, Bk, kh, kw, border, same, st);
 }
 
 template <typename T>

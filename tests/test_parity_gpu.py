@@ -439,3 +439,25 @@ def test_tiled_backward_720p_vs_cpu_oracle():
     gs_ref, gm_ref = run(R, smooth, M.cpu(), target)
     assert rel_l2(gs.cpu(), gs_ref) < 1e-4, rel_l2(gs.cpu(), gs_ref)
     assert rel_l2(gm.cpu(), gm_ref) < 1e-3, rel_l2(gm.cpu(), gm_ref)  # CPU-vs-CUDA reference itself: ~1e-4
+
+
+@pytest.mark.parametrize("border", ["constant", "reflect", "replicate"])
+@pytest.mark.parametrize("k", [3, 5, 7])
+def test_tiled_filter2d_bit_identical_to_generic(k, border):
+    import os
+
+    g = torch.Generator().manual_seed(10 + k)
+    for (B, C, H, W) in ((2, 3, 70, 200), (1, 1, 32, 128), (4, 2, 45, 132), (1, 3, 6 + k, 12)):
+        x = torch.rand(B, C, H, W, generator=g).to(DEV)
+        for kern in (torch.randn(1, k, k, generator=g), torch.randn(B, k, k, generator=g)):
+            kern = kern.to(DEV)
+            for normalized, behaviour in ((False, "corr"), (True, "conv")):
+                a = K.filter2d(x, kern, border, normalized=normalized, behaviour=behaviour)
+                os.environ["KB200_DISABLE_TILED_FILTER"] = "1"
+                try:
+                    b = K.filter2d(x, kern, border, normalized=normalized, behaviour=behaviour)
+                finally:
+                    del os.environ["KB200_DISABLE_TILED_FILTER"]
+                assert torch.equal(a, b), (B, C, H, W, float((a - b).abs().max()))
+                want = R.filter2d(x.cpu(), kern.cpu(), border, normalized=normalized, behaviour=behaviour)
+                torch.testing.assert_close(a.cpu(), want, rtol=1e-4, atol=1e-5)
