@@ -10,6 +10,7 @@
 #include "warp_bwd_tma.cuh"
 #include "sepfilter_tiled.cuh"
 #include "filter2d_tiled.cuh"
+#include "remap_tiled.cuh"
 
 namespace kb200 {
 
@@ -241,8 +242,12 @@ int kb200_remap_forward(const void* src, const void* map_x, const void* map_y, v
   if (rc) return rc;
   KB_CHECK_ARG(map_x && map_y && out, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == KB200_F32)
+  if (dtype == KB200_F32) {
+    rc = remap_tiled_forward((const float*)src, (const float*)map_x, (const float*)map_y, (float*)out, B, C, H, W, h, w, Bmap, normalized,
+                             interp, pad, align_corners, st);
+    if (rc != KB200_EUNSUPPORTED) return rc;
     return remap_forward_t<float>(src, map_x, map_y, out, B, C, H, W, h, w, Bmap, normalized, interp, pad, align_corners, st);
+  }
   return remap_forward_t<double>(src, map_x, map_y, out, B, C, H, W, h, w, Bmap, normalized, interp, pad, align_corners, st);
 }
 

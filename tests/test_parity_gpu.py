@@ -176,8 +176,8 @@ def _bench_homographies(B, H, W, seed, sigma=8.0):
     return bench.perspective_from_quads(quad, quad + sigma * torch.randn(B, 4, 2, generator=g))
 
 
-def _generic(fn):
-    """Run ``fn`` with the tiled kernel disabled (the C ABI then dispatches the generic kernel)."""
+def _generic(fn, check_variant=True):
+    """Run ``fn`` with the tiled kernels disabled (the C ABI then dispatches the generic kernels)."""
     import os
 
     from kornia_b200 import _lib
@@ -185,7 +185,8 @@ def _generic(fn):
     os.environ["KB200_DISABLE_TMA"] = "1"
     try:
         out = fn()
-        assert _lib.last_warp_variant() == "generic"
+        if check_variant:  # only kb200_warp_forward records the variant it dispatched to
+            assert _lib.last_warp_variant() == "generic"
     finally:
         del os.environ["KB200_DISABLE_TMA"]
     return out
@@ -461,3 +462,30 @@ def test_tiled_filter2d_bit_identical_to_generic(k, border):
                 assert torch.equal(a, b), (B, C, H, W, float((a - b).abs().max()))
                 want = R.filter2d(x.cpu(), kern.cpu(), border, normalized=normalized, behaviour=behaviour)
                 torch.testing.assert_close(a.cpu(), want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("pad", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("ac", [None, True])
+@pytest.mark.parametrize("C", [3, 1])
+def test_tiled_remap_bit_identical_to_generic(pad, ac, C):
+    """Smooth maps (served from the staged box), a noisy map (mostly exact path), out-of-view and NaN entries."""
+    H, W, h, w = 96, 160, 80, 136
+    g = torch.Generator().manual_seed(4)
+    img = torch.rand(3, C, H, W, generator=g).to(DEV)
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    smooth_x = xs * (W / w) + 3.0 * torch.sin(ys / 9.0) - 4.0
+    smooth_y = ys * (H / h) + 2.5 * torch.cos(xs / 11.0) + 1.0
+    noisy_x = smooth_x + 30.0 * torch.randn(h, w, generator=g)
+    noisy_y = smooth_y + 30.0 * torch.randn(h, w, generator=g)
+    far_x = smooth_x + 5000.0
+    bad_x = smooth_x.clone()
+    bad_x[::7, ::5] = float("nan")
+    mx = torch.stack([smooth_x, noisy_x, bad_x]).to(DEV)
+    my = torch.stack([smooth_y, noisy_y, smooth_y]).to(DEV)
+    for (ax, ay) in ((mx, my), (far_x[None].to(DEV), smooth_y[None].to(DEV)), (smooth_x[None].to(DEV), smooth_y[None].to(DEV))):
+        a = K.remap(img, ax, ay, padding_mode=pad, align_corners=ac)
+        b = _generic(lambda: K.remap(img, ax, ay, padding_mode=pad, align_corners=ac), check_variant=False)
+        assert torch.equal(a.nan_to_num(nan=-7.0), b.nan_to_num(nan=-7.0)), float((a - b).abs().nan_to_num().max())
+    want = R.remap(img.cpu()[:1], smooth_x[None], smooth_y[None], padding_mode=pad, align_corners=ac)
+    got = K.remap(img[:1], smooth_x[None].to(DEV), smooth_y[None].to(DEV), padding_mode=pad, align_corners=ac)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)

@@ -26,3 +26,18 @@ for k in (3, 5, 11, 17):
     a = t(f)
     gbs = 24.0 * B * 1080 * 1920 / a / 1e6
     print(f"gaussian_blur2d {k}x{k} separable: {a:.3f} ms ({gbs:.0f} GB/s, {gbs/6568*100:.1f}%)", flush=True)
+# remap with a smooth (undistortion-like) map
+ys, xs = torch.meshgrid(torch.arange(1080, dtype=torch.float32, device=dev), torch.arange(1920, dtype=torch.float32, device=dev), indexing="ij")
+r2 = ((xs - 960) / 960) ** 2 + ((ys - 540) / 540) ** 2
+mx = (960 + (xs - 960) * (1 + 0.02 * r2))[None].contiguous()
+my = (540 + (ys - 540) * (1 + 0.02 * r2))[None].contiguous()
+f = lambda: K.remap(x, mx, my, align_corners=True)
+a = t(f)
+os.environ["KB200_DISABLE_TMA"] = "1"; b = t(f, 3); del os.environ["KB200_DISABLE_TMA"]
+gbs = 24.0 * B * 1080 * 1920 / a / 1e6   # shared map: 8 B/pixel of map traffic is read once and stays in L2
+print(f"remap (shared radial map): tiled {a:.3f} ms ({gbs:.0f} GB/s of image traffic, {gbs/6568*100:.1f}%)  generic {b:.3f} ms  x{b/a:.2f}", flush=True)
+mxb, myb = mx.expand(B, -1, -1).contiguous(), my.expand(B, -1, -1).contiguous()
+f = lambda: K.remap(x, mxb, myb, align_corners=True)
+a = t(f)
+gbs = 32.0 * B * 1080 * 1920 / a / 1e6
+print(f"remap (per-sample maps): tiled {a:.3f} ms ({gbs:.0f} GB/s, {gbs/6568*100:.1f}%)", flush=True)
