@@ -85,6 +85,11 @@ def _opaque(fn):
         return fn
 
 
+class Unsupported(RuntimeError):
+    """The C entry point declined a valid request (status KB200_EUNSUPPORTED): the caller may route it
+    through other entry points of the library."""
+
+
 @_opaque
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and turn a non-zero status into ``RuntimeError``."""
@@ -92,7 +97,7 @@ def call(name: str, *args) -> None:
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.kb200_last_error().decode(errors="replace")
-        raise RuntimeError(f"{name} failed (status {rc}): {msg}")
+        raise (Unsupported if rc == -3 else RuntimeError)(f"{name} failed (status {rc}): {msg}")
 
 
 def last_warp_variant() -> str:

@@ -87,10 +87,13 @@ class WarpFunction(torch.autograd.Function):
         fill_c = None if fill is None else fill.to(device=src.device, dtype=src.dtype).contiguous()
         B, C, H, W = src_c.shape
         out = torch.empty((B, C, h, w), device=src.device, dtype=src.dtype)
-        with torch.cuda.device(src.device), _Timed("warp_forward", src):
-            _lib.call("kb200_warp_forward", _ptr(src_c), _ptr(m_c), _ptr(bx), _ptr(by), _ptr(fill_c), _ptr(out),
-                      B, C, H, W, h, w, m_c.shape[0], int(projective), interp, pad, int(align), dt, _stream(src))
-        _bump()
+        if out.numel() > 0 and src_c.numel() > 0:
+            with torch.cuda.device(src.device), _Timed("warp_forward", src):
+                _lib.call("kb200_warp_forward", _ptr(src_c), _ptr(m_c), _ptr(bx), _ptr(by), _ptr(fill_c), _ptr(out),
+                          B, C, H, W, h, w, m_c.shape[0], int(projective), interp, pad, int(align), dt, _stream(src))
+            _bump()
+        else:
+            out.zero_()
         ctx.save_for_backward(src_c, m_c, bx, by, fill_c if fill_c is not None else torch.empty(0, device=src.device))
         ctx.cfg = (h, w, int(projective), interp, pad, int(align), dt, fill_c is not None)
         return out
@@ -105,6 +108,8 @@ class WarpFunction(torch.autograd.Function):
         B, C, H, W = src.shape
         gout = gout.contiguous()
         gsrc = torch.zeros_like(src) if need_src else None
+        if gout.numel() == 0 or src.numel() == 0:
+            return (gsrc, torch.zeros_like(m) if need_m else None) + (None,) * 9
         gm = ws = None
         if need_m:
             gm = torch.empty_like(m)
@@ -181,11 +186,12 @@ class Filter2dFunction(torch.autograd.Function):
             # the reference's view(-1, Bk*C, H, W) (filter.py:142) fails the same way
             raise RuntimeError(f"shape '[-1, {Bk * C}, {H}, {W}]' is invalid for input of size {xc.numel()}")
         Ho, Wo = (H, W) if same else (H - kh + 1, W - kw + 1)
-        out = torch.empty((B, C, Ho, Wo), device=x.device, dtype=x.dtype)
-        with torch.cuda.device(x.device):
-            _lib.call("kb200_filter2d_forward", _ptr(xc), _ptr(kc), _ptr(out), B, C, H, W, Bk, kh, kw, border, int(same), dt,
-                      _stream(x))
-        _bump()
+        out = torch.empty((B, C, max(Ho, 0), max(Wo, 0)), device=x.device, dtype=x.dtype)
+        if out.numel() > 0:
+            with torch.cuda.device(x.device):
+                _lib.call("kb200_filter2d_forward", _ptr(xc), _ptr(kc), _ptr(out), B, C, H, W, Bk, kh, kw, border, int(same), dt,
+                          _stream(x))
+            _bump()
         ctx.save_for_backward(xc, kc)
         ctx.cfg = (border, int(same), dt)
         return out
@@ -229,10 +235,16 @@ class SepFilterFunction(torch.autograd.Function):
             raise RuntimeError(f"shape '[-1, {max(Bkx, Bky) * C}, {H}, {W}]' is invalid for input of size {xc.numel()}")
         Ho, Wo = (H, W) if same else (H - kh + 1, W - kw + 1)
         out = torch.empty((B, C, Ho, Wo), device=x.device, dtype=x.dtype)
-        with torch.cuda.device(x.device), _Timed("sepfilter_forward", x):
-            _lib.call("kb200_sepfilter_forward", _ptr(xc), _ptr(kxc), _ptr(kyc), _ptr(out), B, C, H, W, Bkx, kw, Bky, kh, border,
-                      int(same), dt, _stream(x))
-        _bump()
+        if out.numel() > 0:
+            try:
+                with torch.cuda.device(x.device), _Timed("sepfilter_forward", x):
+                    _lib.call("kb200_sepfilter_forward", _ptr(xc), _ptr(kxc), _ptr(kyc), _ptr(out), B, C, H, W, Bkx, kw, Bky, kh, border,
+                              int(same), dt, _stream(x))
+                _bump()
+            except _lib.Unsupported:
+                # kernels too large for the one-pass shared-memory tile: two 1-D passes of the 2-D kernel
+                mid = Filter2dFunction.apply(xc, kxc[:, None, :], border, same)
+                out = Filter2dFunction.apply(mid, kyc[:, :, None], border, same)
         ctx.save_for_backward(xc, kxc, kyc)
         ctx.cfg = (border, int(same))
         return out

@@ -73,4 +73,14 @@ __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per device: remember, per kernel instantiation, on which devices it was applied
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 }  // namespace kb200

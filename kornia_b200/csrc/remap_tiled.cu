@@ -7,10 +7,9 @@ template <int NC, int PAD, bool ALIGN>
 static int launch_remap_tiled(const CUtensorMap& map, const RemapTiledParams& p, cudaStream_t st) {
   auto kern = remap_tiled_kernel<NC, PAD, ALIGN>;
   constexpr size_t smem = (size_t)NC * 72 * 40 * 4 + 8 + 32 * 4 + 4 * 4 + 16;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;  // per instantiation, one bit per device
+  if (first_use_on_device(configured)) {
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const dim3 grid(ceil_div(p.w, 64), ceil_div(p.h, 32), p.B);
   kern<<<grid, 256, smem, st>>>(map, p);

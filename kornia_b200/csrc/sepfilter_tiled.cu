@@ -8,10 +8,9 @@ static int launch_sep_tiled(const CUtensorMap& map, const SepTiledParams& p, cud
   constexpr int BH = SEPT_TH + K - 1;
   constexpr size_t smem = (size_t)(2 * BH * SEPT_BW + BH * SEPT_TW) * 4 + 2 * sizeof(uint64_t);
   auto kern = sepfilter_tiled_kernel<K, BORDER>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;  // per instantiation, one bit per device
+  if (first_use_on_device(configured)) {
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const long long nstrips = (long long)p.planes * ceil_div(p.H, SEPT_TH);
   const long long cap = 3ll * sm_count();

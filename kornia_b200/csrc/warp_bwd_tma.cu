@@ -9,10 +9,9 @@ static int launch_warp_bwd_tma(const CUtensorMap& msrc, const CUtensorMap& mgsrc
   auto kern = warp_bwd_tma<NC, PAD, PROJ, ALIGN, NEED_SRC, NEED_M>;
   constexpr size_t smem = (size_t)(NEED_M ? NC * 72 * 40 * 4 : 0) + (size_t)TMA_CONSUMER_WARPS * NC * 72 * BWD_SH * 4 + 2 * sizeof(uint64_t) +
                           sizeof(BwdStageInfo) + 64;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;  // per instantiation, one bit per device
+  if (first_use_on_device(configured)) {
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   kern<<<bwd_tma_grid(p.B, p.h), TMA_THREADS, smem, st>>>(msrc, mgsrc, mgout, p);
   cudaError_t e = cudaGetLastError();

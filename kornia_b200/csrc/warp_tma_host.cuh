@@ -14,10 +14,9 @@ template <int NC, int INTERP, int PAD, bool PROJ, bool ALIGN, int TW, int TH, in
 static int launch_warp_tma_cfg(const CUtensorMap& map, const TmaWarpParams& p, int ctas_per_sm, cudaStream_t st) {
   auto kern = warp_fwd_tma<NC, INTERP, PAD, PROJ, ALIGN, TW, TH, BW, BH, NSTAGE>;
   constexpr size_t smem = NSTAGE * (size_t)NC * BW * BH * 4 + 2 * NSTAGE * sizeof(uint64_t) + NSTAGE * sizeof(StageInfo);
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static unsigned long long configured = 0;  // per instantiation, one bit per device
+  if (first_use_on_device(configured)) {
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const long long nstrips = (long long)p.B * ceil_div(p.h, TH);
   const long long cap = (long long)ctas_per_sm * sm_count();

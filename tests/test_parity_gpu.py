@@ -489,3 +489,42 @@ def test_tiled_remap_bit_identical_to_generic(pad, ac, C):
     want = R.remap(img.cpu()[:1], smooth_x[None], smooth_y[None], padding_mode=pad, align_corners=ac)
     got = K.remap(img[:1], smooth_x[None].to(DEV), smooth_y[None].to(DEV), padding_mode=pad, align_corners=ac)
     torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ contract details on the device
+def test_noncontiguous_inputs_and_contiguous_outputs():
+    # tests/geometry/transform/test_imgwarp.py:487-489, tests/filters/test_filters.py:359-366: stride-0 expanded inputs
+    img = torch.rand(1, 1, 20, 24, device=DEV).expand(3, 3, -1, -1)
+    M = torch.eye(3, device=DEV)[None].expand(3, -1, -1)
+    out = K.warp_perspective(img, M, (20, 24))
+    assert out.is_contiguous()
+    torch.testing.assert_close(out, img.contiguous(), rtol=1e-4, atol=1e-4)
+    blur = K.gaussian_blur2d(img, (3, 3), (1.0, 1.0))
+    assert blur.is_contiguous() and blur.shape == img.shape
+    f = K.filter2d(img.transpose(-1, -2), torch.ones(1, 3, 3, device=DEV), normalized=True)
+    assert f.is_contiguous()
+    torch.testing.assert_close(f, R.filter2d(img.transpose(-1, -2).cpu(), torch.ones(1, 3, 3), normalized=True).to(DEV), rtol=1e-4, atol=1e-5)
+
+
+def test_empty_batch_and_huge_separable_kernel():
+    e = K.warp_affine(torch.rand(0, 3, 8, 8, device=DEV), torch.zeros(0, 2, 3, device=DEV), (4, 4))
+    assert e.shape == (0, 3, 4, 4)
+    x = torch.rand(1, 1, 160, 160, device=DEV)
+    kx = torch.rand(1, 151, device=DEV)
+    ky = torch.rand(1, 151, device=DEV)
+    got = K.filter2d_separable(x, kx, ky, "constant")  # too large for the one-pass tile: two 1-D passes inside the library
+    want = R.filter2d_separable(x.cpu(), kx.cpu(), ky.cpu(), "constant")
+    assert rel_l2(got.cpu(), want) < 1e-5
+
+
+def test_second_device_if_present():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("single GPU")
+    d1 = torch.device("cuda:1")
+    x = torch.rand(2, 3, 64, 128, device=d1)
+    M = torch.eye(3, device=d1)[None].repeat(2, 1, 1)
+    M[:, 0, 2] = 2.0
+    a = K.warp_perspective(x, M, (64, 128))
+    b = K.gaussian_blur2d(x, (5, 5), (1.0, 1.0))
+    assert a.device == d1 and b.device == d1
+    torch.testing.assert_close(a.cpu(), R.warp_perspective(x.cpu(), M.cpu(), (64, 128)), rtol=1e-4, atol=1e-5)
