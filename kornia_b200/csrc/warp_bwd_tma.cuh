@@ -47,10 +47,10 @@ struct BwdStageInfo {
 // One pixel handled entirely through global memory: exact scatter with bounds tests and, when
 // requested, the coordinate gradient from global taps.  Returns (gix, giy).
 template <int NC, int PAD, bool NEED_SRC, bool NEED_M>
-__device__ __noinline__ float2 bwd_pixel_global(const TmaBwdParams& p, int b, const float* __restrict__ gop, size_t oplane, float ix,
-                                                float iy) {
+__device__ __noinline__ float2 bwd_pixel_global(const TmaBwdParams& p, int b, int y, int x, float ix, float iy) {
   const int H = p.H, W = p.W;
-  const size_t splane = (size_t)H * W;
+  const size_t splane = (size_t)H * W, oplane = (size_t)p.h * p.w;
+  const float* gop = p.gout + (size_t)b * NC * oplane + (size_t)y * p.w + x;
   ix = guard_index(ix);  // NaN / inf / beyond int range -> out of bounds, as in the generic kernel
   iy = guard_index(iy);
   const float x0f = floorf(ix), y0f = floorf(iy);
@@ -313,7 +313,6 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) warp_bwd_tma(const __grid_cons
           if (NEED_M) ok = ok && ix >= lo_x && ix < hi_x && iy >= lo_y && iy < hi_y;
           const int Xl = __shfl_up_sync(0xffffffffu, X, 1), Yl = __shfl_up_sync(0xffffffffu, Y, 1);
           if (lane > 0 && Xl == X && Yl == Y) ok = false;
-          const float* gop = gbase + (size_t)min(y, p.h - 1) * p.w + min(x, p.w - 1);
           float gix = 0.f, giy = 0.f;
           if (__all_sync(0xffffffffu, ok)) {
             const float x0f = R::sub(tX, FLOOR_MAGIC), y0f = R::sub(tY, FLOOR_MAGIC);
@@ -355,7 +354,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) warp_bwd_tma(const __grid_cons
             }
           } else if (live) {
             // exact per-pixel path (the unpadded coordinate is re-clamped inside for 'border')
-            const float2 g = bwd_pixel_global<NC, PAD, NEED_SRC, NEED_M>(p, b, gop, oplane, ix, iy);
+            const float2 g = bwd_pixel_global<NC, PAD, NEED_SRC, NEED_M>(p, b, y, x, ix, iy);
             gix = g.x;
             giy = g.y;
           }
