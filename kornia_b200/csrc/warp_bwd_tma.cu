@@ -13,7 +13,7 @@ static int launch_warp_bwd_tma(const CUtensorMap& msrc, const CUtensorMap& mgsrc
   if (first_use_on_device(configured)) {
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  kern<<<bwd_tma_grid(p.B, p.h), TMA_THREADS, smem, st>>>(msrc, mgsrc, mgout, p);
+  kern<<<bwd_tma_grid(p.B, p.h), BWD_THREADS, smem, st>>>(msrc, mgsrc, mgout, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("warp_bwd_tma launch failed: %s", cudaGetErrorString(e));
@@ -66,6 +66,10 @@ int warp_tma_backward(const float* gout, const float* src, const float* m, const
   p.gout = gout; p.src = src; p.m = m; p.bx = bx; p.by = by; p.gsrc = gsrc;
   p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = Bm;
   p.max_segs = bwd_tma_max_segs(B, h);
+  {
+    const char* dbg = getenv("KB200_BWD_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   const size_t rows = (size_t)bwd_tma_grid(B, h) * p.max_segs;
   if (gm) {
     p.records = reinterpret_cast<float*>(workspace);

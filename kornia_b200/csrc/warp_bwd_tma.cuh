@@ -33,9 +33,11 @@ struct TmaBwdParams {
   float* records;      // (grid, max_segs, 8 warps, 9) partial sums for d/dm, or null
   int* record_batch;   // (grid, max_segs) batch index of each record row, -1 = unused
   int B, H, W, h, w, Bm, max_segs;
+  int debug;  // measurement aid (KB200_BWD_DEBUG): 1 skip the strip flush, 2 also skip the strip adds, 4 skip the d/dM taps
 };
 
-constexpr int BWD_SH = 8;  // rows of a warp's accumulation strip
+constexpr int BWD_SH = 8;         // rows of a warp's accumulation strip
+constexpr int BWD_THREADS = 256;  // 8 warps; warp 0 doubles as the TMA issuer (a 9th warp would cap registers at 96)
 
 struct BwdStageInfo {
   float lo_x, hi_x, lo_y, hi_y;  // source-box window (as in the forward kernel)
@@ -82,7 +84,7 @@ __device__ __noinline__ float2 bwd_pixel_global(const TmaBwdParams& p, int b, in
 }
 
 template <int NC, int PAD, bool PROJ, bool ALIGN, bool NEED_SRC, bool NEED_M>
-__global__ void __launch_bounds__(TMA_THREADS, 2) warp_bwd_tma(const __grid_constant__ CUtensorMap tmap_src,
+__global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma(const __grid_constant__ CUtensorMap tmap_src,
                                                                const __grid_constant__ CUtensorMap tmap_gsrc,
                                                                const __grid_constant__ CUtensorMap tmap_gout,
                                                                const __grid_constant__ TmaBwdParams p) {
@@ -117,95 +119,113 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) warp_bwd_tma(const __grid_cons
   const int H = p.H, W = p.W;
   const float Wm1 = (float)(W - 1), Hm1 = (float)(H - 1), Wf = (float)W, Hf = (float)H;
 
-  if (warp == TMA_CONSUMER_WARPS) {
-    // ------------------------------------------------------------------ producer warp
-    if (NEED_M && tma::elect_one()) tma::prefetch_map(&tmap_src);
-    uint32_t phase = 0;
-    int strip, tx0, tx1, cursor = 0;
-    for (int seg = 0; segs.get(seg, strip, tx0, tx1, cursor); ++seg) {
-      const int b = strip / tiles_y, ty = strip - b * tiles_y;
-      Mat3<float> m;
-      m.load(p.m + (p.Bm == 1 ? 0 : (size_t)b * 9));
-      // lane = 4 * w + corner: corner (lane & 3) of consumer warp w's 64 x RPW sub-tile
-      const int wsub = lane >> 2;
-      const int py = min(ty * TH + wsub * RPW + ((lane & 2) ? RPW - 1 : 0), p.h - 1);
-      const float byv = __ldg(p.by + py);
-      for (int tx = tx0; tx < tx1; ++tx) {
-        const int px = min(tx * TW + ((lane & 1) ? TW - 1 : 0), p.w - 1);
-        float gx, gy, den;
-        map_point<float, PROJ>(m, __ldg(p.bx + px), byv, gx, gy, den);
-        float ix = unnorm<ALIGN>(gx, Wm1, Wf), iy = unnorm<ALIGN>(gy, Hm1, Hf);
-        bool ok = fabsf(ix) < 4.0e6f && fabsf(iy) < 4.0e6f;
-        if (PROJ) {
-          const unsigned neg = __ballot_sync(0xffffffffu, den < 0.f);
-          ok = ok && (neg == 0u || neg == 0xffffffffu) && fabsf(den) > 1e-12f;
-        }
-        if (PAD == KB200_BORDER) {
-          ix = clip_coord(ix, W);
-          iy = clip_coord(iy, H);
-        }
-        // per-warp (groups of 4 lanes) and whole-tile extrema
-        float lo_x = ix, hi_x = ix, lo_y = iy, hi_y = iy;
+  // ------------------------------------------------------------------ tile look-ahead (warp 0 only)
+  // Warp 0 prepares tile t+1 while everybody works on tile t: it maps the corners of the tile and of every
+  // warp's 64 x RPW sub-tile (lane = 4 * w + corner), pulls the upstream-gradient tile and the source box into
+  // L2, and -- once all warps have released the shared buffers -- publishes the origins and issues the TMA load.
+  struct Next {
+    int seg, strip, tx0, tx1, cursor, tx;
+    bool live;
+    int b, ty, ox, oy, soy_w;
+    bool ok, fits;
+  } nx{0, 0, 0, 0, 0, 0, false, 0, 0, 0, 0, 0, false, false};
+  auto next_advance = [&]() {  // step to the following tile of this CTA's sequence
+    if (nx.live && nx.tx + 1 < nx.tx1) {
+      ++nx.tx;
+      return;
+    }
+    nx.live = segs.get(nx.seg, nx.strip, nx.tx0, nx.tx1, nx.cursor);
+    ++nx.seg;
+    nx.tx = nx.tx0;
+  };
+  auto next_prepare = [&]() {  // corners + L2 prefetch of the tile `nx` points at (all 32 lanes of warp 0)
+    if (!nx.live) return;
+    const int b = nx.strip / tiles_y, ty = nx.strip - b * tiles_y;
+    nx.b = b;
+    nx.ty = ty;
+    Mat3<float> m;
+    m.load(p.m + (p.Bm == 1 ? 0 : (size_t)b * 9));
+    const int wsub = lane >> 2;
+    const int py = min(ty * TH + wsub * RPW + ((lane & 2) ? RPW - 1 : 0), p.h - 1);
+    const int px = min(nx.tx * TW + ((lane & 1) ? TW - 1 : 0), p.w - 1);
+    float gx, gy, den;
+    map_point<float, PROJ>(m, __ldg(p.bx + px), __ldg(p.by + py), gx, gy, den);
+    float ix = unnorm<ALIGN>(gx, Wm1, Wf), iy = unnorm<ALIGN>(gy, Hm1, Hf);
+    bool ok = fabsf(ix) < 4.0e6f && fabsf(iy) < 4.0e6f;
+    if (PROJ) {
+      const unsigned neg = __ballot_sync(0xffffffffu, den < 0.f);
+      ok = ok && (neg == 0u || neg == 0xffffffffu) && fabsf(den) > 1e-12f;
+    }
+    if (PAD == KB200_BORDER) {
+      ix = clip_coord(ix, W);
+      iy = clip_coord(iy, H);
+    }
+    float lo_x = ix, hi_x = ix, lo_y = iy, hi_y = iy;
 #pragma unroll
-        for (int o = 1; o < 4; o <<= 1) {
-          lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
-          hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
-        }
-        const float warp_lo_y = lo_y;
+    for (int o = 1; o < 4; o <<= 1) {
+      lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
+      hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+    }
+    const float warp_lo_y = lo_y;
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
-          hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
-        }
+    for (int o = 4; o < 32; o <<= 1) {
+      lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
+      hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+    }
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
-          hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+    for (int o = 1; o < 32; o <<= 1) {
+      lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
+      hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    const int x_lo = (int)floorf(lo_x), x_hi = (int)floorf(hi_x) + 1;
+    const int y_lo = (int)floorf(lo_y), y_hi = (int)floorf(hi_y) + 1;
+    const int need_w = x_hi - x_lo + 1, need_h = y_hi - y_lo + 1;
+    const int spare = BW - need_w - 3;
+    nx.ox = (x_lo - (spare > 0 ? spare / 2 : 0)) & ~3;  // TMA: 16-byte aligned box start
+    nx.oy = y_lo - (BH - need_h) / 2;
+    nx.ok = ok;
+    nx.fits = ok && x_hi - nx.ox + 1 <= BW && need_h <= BH;
+    // strip origin of sub-tile wsub: clamped to the image (a TMA reduce cannot take negative coordinates)
+    nx.soy_w = ok ? max((int)floorf(warp_lo_y), 0) : 0x20000000;
+    if (tma::elect_one()) {
+      tma::prefetch_3d(&tmap_gout, nx.tx * TW, ty * TH, b * NC);
+      if (NEED_M && nx.fits) tma::prefetch_3d(&tmap_src, nx.ox, nx.oy, b * NC);
+    }
+    __syncwarp();
+  };
+  auto next_publish = [&]() {  // shared buffers are free: origins + the real load (warp 0, converged)
+    if (!nx.live) return;
+    if ((lane & 3) == 0) info->soy[lane >> 2] = nx.soy_w;
+    __syncwarp();  // the elected lane's arrive (release) must cover the other lanes' writes to `info`
+    if (tma::elect_one()) {
+      info->sox = nx.ok ? max(nx.ox, 0) : 0x20000000;
+      if (NEED_M) {
+        if (nx.fits) {
+          info->lo_x = (float)nx.ox;
+          info->hi_x = (float)(nx.ox + BW - 1);
+          info->lo_y = (float)nx.oy;
+          info->hi_y = (float)(nx.oy + BH - 1);
+          info->k = (unsigned)(FLOOR_MAGIC_BITS + nx.oy) * (unsigned)BW + (unsigned)(FLOOR_MAGIC_BITS + nx.ox);
+          tma::mbar_arrive_expect_tx(full, BOX_BYTES);
+          tma::load_3d(box, &tmap_src, full, nx.ox, nx.oy, nx.b * NC);
+        } else {
+          info->lo_x = info->lo_y = 1.f;
+          info->hi_x = info->hi_y = 0.f;
+          info->k = 0;
+          tma::mbar_arrive(full);
         }
-        ok = __all_sync(0xffffffffu, ok);
-        const int x_lo = (int)floorf(lo_x), x_hi = (int)floorf(hi_x) + 1;
-        const int y_lo = (int)floorf(lo_y), y_hi = (int)floorf(hi_y) + 1;
-        const int need_w = x_hi - x_lo + 1, need_h = y_hi - y_lo + 1;
-        const int spare = BW - need_w - 3;
-        const int ox = (x_lo - (spare > 0 ? spare / 2 : 0)) & ~3;
-        const bool fits = ok && x_hi - ox + 1 <= BW && need_h <= BH;
-        const int oy = y_lo - (BH - need_h) / 2;
-        // Everything above ran while the consumers were still busy with the previous tile: pull this tile's
-        // upstream-gradient tile and source box into L2 now, then wait for the shared buffers to be released.
-        if (tma::elect_one()) {
-          tma::prefetch_3d(&tmap_gout, tx * TW, ty * TH, b * NC);
-          if (NEED_M && fits) tma::prefetch_3d(&tmap_src, ox, oy, b * NC);
-        }
-        tma::mbar_wait(empty, phase ^ 1);
-        // strip origin of sub-tile wsub: clamped to the image (a TMA reduce cannot take negative coordinates)
-        if ((lane & 3) == 0) info->soy[wsub] = ok ? max((int)floorf(warp_lo_y), 0) : 0x20000000;
-        __syncwarp();  // the elected lane's arrive (release) must cover the other lanes' writes to `info`
-        if (tma::elect_one()) {
-          info->sox = ok ? max(ox, 0) : 0x20000000;
-          if (NEED_M) {
-            if (fits) {
-              info->lo_x = (float)ox;
-              info->hi_x = (float)(ox + BW - 1);
-              info->lo_y = (float)oy;
-              info->hi_y = (float)(oy + BH - 1);
-              info->k = (unsigned)(FLOOR_MAGIC_BITS + oy) * (unsigned)BW + (unsigned)(FLOOR_MAGIC_BITS + ox);
-              tma::mbar_arrive_expect_tx(full, BOX_BYTES);
-              tma::load_3d(box, &tmap_src, full, ox, oy, b * NC);
-            } else {
-              info->lo_x = info->lo_y = 1.f;
-              info->hi_x = info->hi_y = 0.f;
-              info->k = 0;
-              tma::mbar_arrive(full);
-            }
-          } else {
-            tma::mbar_arrive(full);
-          }
-        }
-        __syncwarp();
-        phase ^= 1;
+      } else {
+        tma::mbar_arrive(full);
       }
     }
-    return;
+    __syncwarp();
+  };
+  if (warp == 0) {  // first tile: nothing to wait for
+    if (NEED_M && tma::elect_one()) tma::prefetch_map(&tmap_src);
+    next_advance();
+    next_prepare();
+    next_publish();
   }
 
   // -------------------------------------------------------------------- consumer warps
@@ -226,6 +246,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) warp_bwd_tma(const __grid_cons
     const float ux_scale = ALIGN ? Wm1 * 0.5f : Wf * 0.5f, uy_scale = ALIGN ? Hm1 * 0.5f : Hf * 0.5f;
 
     for (int tx = tx0; tx < tx1; ++tx) {
+      if (warp == 0) {  // look one tile ahead
+        next_advance();
+        next_prepare();
+      }
       // lane <-> output columns (2 lane, 2 lane + 1): inside one instruction the lanes are two pixels apart, so
       // their floor cells are distinct whenever the source step per output pixel exceeds 1/2
       const int x0 = tx * TW + 2 * lane;
@@ -321,7 +345,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) warp_bwd_tma(const __grid_cons
             float go[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) go[c] = j == 0 ? go2[c].x : go2[c].y;
-            if (NEED_SRC) {
+            if (NEED_SRC && !(p.debug & 2)) {
               const uint32_t a = ((unsigned)Y * (unsigned)BW + (unsigned)X) * 4u + strip_base;
               // tap by tap: lanes hit distinct cells inside one instruction; __syncwarp orders the taps
 #pragma unroll
@@ -338,7 +362,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) warp_bwd_tma(const __grid_cons
                 tma::sts(a + (c * SPLANE + BW + 1) * 4, tma::lds(a + (c * SPLANE + BW + 1) * 4) + w_se * go[c]);
               __syncwarp();
             }
-            if (NEED_M) {
+            if (NEED_M && !(p.debug & 4)) {
               const uint32_t t = ((unsigned)Y * (unsigned)BW + (unsigned)X) * 4u + box_base;
               // s_tap = sum_c gout[c] * src[c, tap]; then the two bilinear derivatives
               float s_nw = 0.f, s_ne = 0.f, s_sw = 0.f, s_se = 0.f;
@@ -370,18 +394,22 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) warp_bwd_tma(const __grid_cons
           }
         }
       }
-      // release the source box, flush the strip
+      // release the shared buffers, flush the strip
       __syncwarp();
       if (lane == 0) tma::mbar_arrive(empty);
       if (NEED_SRC) {
         tma::fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && sox < 0x10000000 && soy < 0x10000000) {
+        if (lane == 0 && sox < 0x10000000 && soy < 0x10000000 && !(p.debug & 3)) {
           asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmap_gsrc),
                        "r"(strip_u32), "r"(sox), "r"(soy), "r"(b * NC)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+      }
+      if (warp == 0) {  // when every warp has released this tile: publish + load the next one
+        tma::mbar_wait(empty, phase);
+        next_publish();
       }
       phase ^= 1;
     }

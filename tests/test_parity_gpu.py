@@ -528,3 +528,24 @@ def test_second_device_if_present():
     b = K.gaussian_blur2d(x, (5, 5), (1.0, 1.0))
     assert a.device == d1 and b.device == d1
     torch.testing.assert_close(a.cpu(), R.warp_perspective(x.cpu(), M.cpu(), (64, 128)), rtol=1e-4, atol=1e-5)
+
+
+def test_tiled_backward_shared_affine_matrix():
+    """warp_affine with one (1,2,3) matrix for the whole batch: d/dM sums over the batch (imgwarp.py:282-283)."""
+    H, W, B = 64, 128, 5
+    g = torch.Generator().manual_seed(3)
+    src = torch.rand(B, 3, H, W, generator=g).to(DEV)
+    A = torch.tensor([[[0.98, 0.05, 1.5], [-0.04, 1.01, -2.0]]], device=DEV)
+    cot = (torch.rand(B, 3, H, W, generator=g) - 0.5).to(DEV)
+
+    def grads():
+        s, a = src.clone().requires_grad_(True), A.clone().requires_grad_(True)
+        return torch.autograd.grad(K.warp_affine(s, a, (H, W)), [s, a], grad_outputs=cot)
+
+    gs, ga = grads()
+    gs_ref, ga_ref = _generic(grads)
+    assert ga.shape == (1, 2, 3)
+    assert rel_l2(gs, gs_ref) < 2e-6 and rel_l2(ga, ga_ref) < 1e-4
+    s, a = src.cpu().requires_grad_(True), A.cpu().requires_grad_(True)
+    gs_cpu, ga_cpu = torch.autograd.grad(R.warp_affine(s, a, (H, W)), [s, a], grad_outputs=cot.cpu())
+    assert rel_l2(gs.cpu(), gs_cpu) < 1e-4 and rel_l2(ga.cpu(), ga_cpu) < 1e-3
