@@ -125,6 +125,24 @@ int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* ker
                             void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Image derivatives: spatial_gradient / sobel (filters/sobel.py:32-74,134-167:
+ * F.pad(replicate) + F.conv2d with a (nout,1,k,k) weight, then for sobel two slices + 5 elementwise
+ * passes).  One kernel: the replicate border is a clamp on the tap index, all nout derivatives of a
+ * pixel come out of one register window.
+ *   x     (planes,H,W) device, planes = B*C
+ *   taps  HOST pointer to nout*k*k doubles, [nout][k][k] correlation taps holding values exactly
+ *         representable in `dtype` (the host builds and normalises them in that dtype:
+ *         filters/kernels.py:504-528, :68-74); k in {3,5}, nout in {2,3}
+ *   out   (planes,nout,H,W); with magnitude=1 (nout=2, k=3): (planes,H,W) = sqrt(gx*gx + gy*gy + eps)
+ * Backward: gx (planes,H,W) = adjoint of (replicate pad, nout correlations) applied to
+ * gout (planes,nout,H,W); deterministic gather.
+ * ------------------------------------------------------------------------------------------ */
+int kb200_spatial_gradient_forward(const void* x, const double* taps, void* out, int planes, int H, int W, int nout,
+                                   int k, int magnitude, double eps, int dtype, void* stream);
+int kb200_spatial_gradient_backward(const void* gout, const double* taps, void* gx, int planes, int H, int W,
+                                    int nout, int k, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Diagnostics (used by tests/): counts elements where the shared-reciprocal division of the tiled
  * warp kernel differs from IEEE division in a way that could change a sampled pixel.  `count`
  * (device int, zeroed by the caller) is incremented atomically.

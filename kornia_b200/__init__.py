@@ -19,26 +19,38 @@ _PATCHED = {}
 
 
 def install(kornia_module=None) -> None:
-    """Rebind the six hot-path functions on an imported ``kornia`` package (every re-export site:
-    geometry/transform/__init__.py:30, geometry/__init__.py:40, filters/__init__.py:37-38 and the
-    defining modules, so internal callers such as ``GaussianBlur2d`` / ``RandomPerspective`` pick
-    them up).  ``uninstall()`` restores the originals."""
+    """Rebind the hot-path functions on an imported ``kornia`` package.
+
+    Every module of the package that holds a reference to one of the originals is patched: the
+    defining modules and re-export sites (geometry/transform/__init__.py:30, geometry/__init__.py:40,
+    filters/__init__.py:37-38) and every ``from ... import warp_perspective``-style importer, so the
+    callers either side of the path -- ``RandomPerspective`` / ``RandomAffine`` / ``RandomGaussianBlur``
+    (augmentation/_2d/geometric/perspective.py:108, affine.py:154, _2d/intensity/gaussian_blur.py:108),
+    ``affine`` / ``rotate`` / ``crop_by_transform_mat``, ``GaussianBlur2d``, ``unsharp_mask``, SSIM ... --
+    run on the CUDA kernels without being rewritten.  ``uninstall()`` restores the originals."""
     import importlib
+    import sys
 
     k = kornia_module or importlib.import_module("kornia")
-    sites = {
-        "warp_perspective": (warp_perspective, ["geometry.transform.imgwarp", "geometry.transform", "geometry"]),
-        "warp_affine": (warp_affine, ["geometry.transform.imgwarp", "geometry.transform", "geometry"]),
-        "remap": (remap, ["geometry.transform.imgwarp", "geometry.transform", "geometry"]),
-        "filter2d": (filter2d, ["filters.filter", "filters"]),
-        "filter2d_separable": (filter2d_separable, ["filters.filter", "filters"]),
-        "gaussian_blur2d": (gaussian_blur2d, ["filters.gaussian", "filters"]),
+    prefix = k.__name__ + "."
+    defining = {
+        "warp_perspective": ("geometry.transform.imgwarp", warp_perspective),
+        "warp_affine": ("geometry.transform.imgwarp", warp_affine),
+        "remap": ("geometry.transform.imgwarp", remap),
+        "filter2d": ("filters.filter", filter2d),
+        "filter2d_separable": ("filters.filter", filter2d_separable),
+        "gaussian_blur2d": ("filters.gaussian", gaussian_blur2d),
     }
-    for name, (fn, mods) in sites.items():
-        for mod in mods:
-            m = importlib.import_module(f"{k.__name__}.{mod}")
-            if hasattr(m, name):
-                _PATCHED.setdefault((m, name), getattr(m, name))
+    originals = {}
+    for name, (mod, fn) in defining.items():
+        m = importlib.import_module(prefix + mod)
+        originals[name] = (_PATCHED.get((m, name), getattr(m, name)), fn)
+    for modname, m in list(sys.modules.items()):
+        if m is None or not (modname == k.__name__ or modname.startswith(prefix)):
+            continue
+        for name, (orig, fn) in originals.items():
+            if m.__dict__.get(name) is orig:
+                _PATCHED.setdefault((m, name), orig)
                 setattr(m, name, fn)
 
 

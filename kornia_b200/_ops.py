@@ -2,6 +2,7 @@
 torch's; every FLOP on an image is executed by kornia_b200/csrc kernels."""
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
@@ -264,3 +265,41 @@ class SepFilterFunction(torch.autograd.Function):
             grads = list(torch.autograd.grad(out, wrt, gout.contiguous())) if wrt else []
         res = [grads.pop(0) if n else None for n in need[:3]]
         return res[0], res[1], res[2], None, None
+
+
+class SpatialGradientFunction(torch.autograd.Function):
+    """``nout`` k x k derivative stencils over a replicate border in one kernel: x (B,C,H,W) ->
+    (B,C,nout,H,W), or the Sobel magnitude (B,C,H,W) when ``magnitude`` (forward only).  ``taps`` is
+    a host tuple of nout*k*k floats whose values are exact in x.dtype."""
+
+    @staticmethod
+    def forward(ctx, x, taps, nout, k, magnitude, eps):
+        _require_cuda(x, "input")
+        dt = _dtype_code(x)
+        xc = x.contiguous()
+        B, C, H, W = xc.shape
+        shape = (B, C, H, W) if magnitude else (B, C, nout, H, W)
+        out = torch.empty(shape, device=x.device, dtype=x.dtype)
+        host_taps = (ctypes.c_double * len(taps))(*taps)
+        if out.numel() > 0:
+            with torch.cuda.device(x.device), _Timed("spatial_gradient_forward", x):
+                _lib.call("kb200_spatial_gradient_forward", _ptr(xc), host_taps, _ptr(out), B * C, H, W, nout, k, int(magnitude),
+                          float(eps), dt, _stream(x))
+            _bump()
+        ctx.cfg = (host_taps, nout, k, dt, bool(magnitude))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        host_taps, nout, k, dt, magnitude = ctx.cfg
+        if magnitude:
+            raise RuntimeError("kornia_b200: the fused Sobel magnitude is forward-only; sobel() composes the "
+                               "differentiable path when the input requires grad")
+        gout = gout.contiguous()
+        B, C, _, H, W = gout.shape
+        gx = torch.empty((B, C, H, W), device=gout.device, dtype=gout.dtype)
+        if gx.numel() > 0:
+            with torch.cuda.device(gout.device):
+                _lib.call("kb200_spatial_gradient_backward", _ptr(gout), host_taps, _ptr(gx), B * C, H, W, nout, k, dt, _stream(gout))
+            _bump()
+        return gx, None, None, None, None, None

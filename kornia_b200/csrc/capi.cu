@@ -11,6 +11,7 @@
 #include "sepfilter_tiled.cuh"
 #include "filter2d_tiled.cuh"
 #include "remap_tiled.cuh"
+#include "gradient.cuh"
 
 namespace kb200 {
 
@@ -440,6 +441,18 @@ int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* ker
   return sepfilter_forward_t<double>(x, kernel_x, kernel_y, out, B, C, H, W, Bkx, kw, Bky, kh, border, same, st);
 }
 
+
+int kb200_spatial_gradient_forward(const void* x, const double* taps, void* out, int planes, int H, int W, int nout, int k,
+                                   int magnitude, double eps, int dtype, void* stream) {
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  return spatial_gradient_forward(x, taps, out, planes, H, W, nout, k, magnitude, eps, dtype, (cudaStream_t)stream);
+}
+
+int kb200_spatial_gradient_backward(const void* gout, const double* taps, void* gx, int planes, int H, int W, int nout, int k,
+                                    int dtype, void* stream) {
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  return spatial_gradient_backward(gout, taps, gx, planes, H, W, nout, k, dtype, (cudaStream_t)stream);
+}
 
 int kb200_warp_prelude(const void* M, void* m_out, int B, int rows, int H, int W, int h, int w, int dtype, int variant,
                        void* stream) {

@@ -258,3 +258,209 @@ def gaussian_blur2d(input, kernel_size, sigma, border_type="reflect", separable=
         kernel_y = gaussian_taps(int(ky), sigma[:, 0].view(bs, 1))
         return filter2d_separable(input, kernel_x, kernel_y, border_type)
     return filter2d(input, gaussian_kernel2d((ky, kx), sigma), border_type)
+
+
+# --------------------------------------------------------------------------------------
+# filter family on the same loaders
+# --------------------------------------------------------------------------------------
+def box_blur(input, kernel_size, border_type="reflect", separable=False):
+    """kornia/filters/blur.py:62-76 with the box taps of kernels.py:314-315,331-333 (1/k, 1/(ky*kx))."""
+    ky, kx = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
+    if separable:
+        tx = torch.full((1, int(kx)), 1.0 / int(kx), device=input.device, dtype=input.dtype)
+        ty = torch.full((1, int(ky)), 1.0 / int(ky), device=input.device, dtype=input.dtype)
+        return filter2d_separable(input, tx, ty, border_type)
+    taps = torch.full((1, int(ky), int(kx)), 1.0 / (int(kx) * int(ky)), device=input.device, dtype=input.dtype)
+    return filter2d(input, taps, border_type)
+
+
+def laplacian(input, kernel_size, border_type="reflect", normalized=True):
+    """kornia/filters/laplacian.py:59-63 with kernels.py:831-838 (ones, centre = 1 - sum)."""
+    ky, kx = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
+    taps = torch.ones((int(ky), int(kx)), device=input.device, dtype=input.dtype)
+    taps[int(ky) // 2, int(kx) // 2] = 1 - taps.sum()
+    return filter2d(input, taps[None], border_type, normalized=normalized)
+
+
+def unsharp_mask(input, kernel_size, sigma, border_type="reflect"):
+    """kornia/filters/unsharp.py:53-54."""
+    return torch.lerp(gaussian_blur2d(input, kernel_size, sigma, border_type), input, weight=2.0)
+
+
+_D1 = {"sobel": [[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]],
+       "diff": [[0.0, 0.0, 0.0], [-1.0, 0.0, 1.0], [0.0, 0.0, 0.0]]}
+_D2 = {"sobel": ([[-1.0, 0.0, 2.0, 0.0, -1.0], [-4.0, 0.0, 8.0, 0.0, -4.0], [-6.0, 0.0, 12.0, 0.0, -6.0],
+                  [-4.0, 0.0, 8.0, 0.0, -4.0], [-1.0, 0.0, 2.0, 0.0, -1.0]],
+                 [[-1.0, -2.0, 0.0, 2.0, 1.0], [-2.0, -4.0, 0.0, 4.0, 2.0], [0.0, 0.0, 0.0, 0.0, 0.0],
+                  [2.0, 4.0, 0.0, -4.0, -2.0], [1.0, 2.0, 0.0, -2.0, -1.0]]),
+       "diff": ([[0.0, 0.0, 0.0], [1.0, -2.0, 1.0], [0.0, 0.0, 0.0]], [[-1.0, 0.0, 1.0], [0.0, 0.0, 0.0], [1.0, 0.0, -1.0]])}
+
+
+def derivative_taps(mode: str, order: int, device, dtype) -> torch.Tensor:
+    """kornia/filters/kernels.py:357-398,470-528: (2,3,3) [d/dx, d/dy] or (3,k,k) [dxx, dxy, dyy]."""
+    if order == 1:
+        kx = torch.tensor(_D1[mode], device=device, dtype=dtype)
+        return torch.stack([kx, kx.t()])
+    xx, xy = (torch.tensor(t, device=device, dtype=dtype) for t in _D2[mode])
+    return torch.stack([xx, xy, xx.t()])
+
+
+def spatial_gradient(input, mode="sobel", order=1, normalized=True):
+    """kornia/filters/sobel.py:59-74: replicate pad of k//2, conv2d with the (nout,1,k,k) weight."""
+    taps = derivative_taps(mode, order, input.device, input.dtype)
+    if normalized:
+        taps = taps / taps.abs().sum(dim=-1).sum(dim=-1)[..., None, None]
+    b, c, h, w = input.shape
+    half_h, half_w = taps.size(1) // 2, taps.size(2) // 2
+    padded = F.pad(input.reshape(b * c, 1, h, w), [half_h, half_h, half_w, half_w], "replicate")
+    out = F.conv2d(padded, taps[:, None], padding=0, stride=1)
+    return out.reshape(b, c, taps.shape[0], h, w)
+
+
+def sobel(input, normalized=True, eps=1e-6):
+    """kornia/filters/sobel.py:158-167."""
+    edges = spatial_gradient(input, normalized=normalized)
+    gx, gy = edges[:, :, 0], edges[:, :, 1]
+    return torch.sqrt(gx * gx + gy * gy + eps)
+
+
+# --------------------------------------------------------------------------------------
+# callers of the warps (SURVEY.md 8f rows 1-2): matrix builders + affine / crop wrappers
+# --------------------------------------------------------------------------------------
+def rotation_matrix2d(center, angle_deg, scale):
+    """kornia/geometry/transform/imgwarp.py:607-622 (T(c) @ R @ S @ T(-c)) with
+    conversions.py:148 (deg2rad through the fp32 pi) and :1685-1688 ([[c, s], [-s, c]])."""
+    n = center.shape[0]
+    eye = torch.eye(3, device=center.device, dtype=center.dtype)[None].repeat(n, 1, 1)
+    t_fwd, t_back, s_m, r_m = eye.clone(), eye.clone(), eye.clone(), eye.clone()
+    t_fwd[:, :2, 2] = center
+    t_back[:, :2, 2] = -center
+    s_m[:, 0, 0] *= scale[:, 0]
+    s_m[:, 1, 1] *= scale[:, 1]
+    rad = angle_deg * torch.tensor(3.14159265358979323846).to(angle_deg.device).type(angle_deg.dtype) / 180.0
+    c, s = torch.cos(rad), torch.sin(rad)
+    r_m[:, :2, :2] = torch.stack([c, s, -s, c], dim=-1).view(n, 2, 2)
+    return (t_fwd @ r_m @ s_m @ t_back)[:, :2, :]
+
+
+def affine(tensor, matrix, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """kornia/geometry/transform/affwarp.py:172-193."""
+    single = tensor.dim() == 3
+    if single:
+        tensor = tensor[None]
+    if tensor.shape[0] == 1 and matrix.shape[0] != 1:
+        tensor = tensor.expand(matrix.shape[0], -1, -1, -1)
+    matrix = matrix.expand(tensor.shape[0], -1, -1)
+    out = warp_affine(tensor, matrix, tuple(tensor.shape[-2:]), mode, padding_mode, align_corners)
+    return out[0] if single else out
+
+
+def _center_xy(tensor):
+    h, w = tensor.shape[-2:]
+    return torch.tensor([float(w - 1) / 2, float(h - 1) / 2], device=tensor.device, dtype=tensor.dtype)
+
+
+def rotate(tensor, angle, center=None, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """kornia/geometry/transform/affwarp.py:312-325."""
+    center = _center_xy(tensor) if center is None else center
+    angle = angle.expand(tensor.shape[0])
+    center = center.expand(tensor.shape[0], -1)
+    return affine(tensor, rotation_matrix2d(center, angle, torch.ones_like(center)), mode, padding_mode, align_corners)
+
+
+def translate(tensor, translation, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """kornia/geometry/transform/affwarp.py:105-112,446-452."""
+    m = torch.eye(3, device=translation.device, dtype=translation.dtype)[None].repeat(translation.shape[0], 1, 1)
+    m[..., 0, 2:3] += translation[..., 0:1]
+    m[..., 1, 2:3] += translation[..., 1:2]
+    return affine(tensor, m[..., :2, :3], mode, padding_mode, align_corners)
+
+
+def scale(tensor, scale_factor, center=None, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """kornia/geometry/transform/affwarp.py:115-119,504-519."""
+    if scale_factor.dim() == 1:
+        scale_factor = scale_factor.repeat(1, 2)
+    center = _center_xy(tensor) if center is None else center
+    center = center.expand(tensor.shape[0], -1)
+    scale_factor = scale_factor.expand(tensor.shape[0], 2)
+    zero = torch.zeros(scale_factor.shape[:1], device=scale_factor.device, dtype=scale_factor.dtype)
+    return affine(tensor, rotation_matrix2d(center, zero, scale_factor), mode, padding_mode, align_corners)
+
+
+def shear(tensor, shear, mode="bilinear", padding_mode="zeros", align_corners=False):
+    """kornia/geometry/transform/affwarp.py:122-133,566-573."""
+    m = torch.eye(3, device=shear.device, dtype=shear.dtype)[None].repeat(shear.shape[0], 1, 1)
+    m[..., 0, 1:2] += shear[..., 0:1]
+    m[..., 1, 0:1] += shear[..., 1:2]
+    return affine(tensor, m[..., :2, :3], mode, padding_mode, align_corners)
+
+
+def square_to_quad(pts):
+    """kornia/geometry/transform/imgwarp.py:411-441: unit square -> quadrilateral, Heckbert's closed form."""
+    (x0, y0), (x1, y1), (x2, y2), (x3, y3) = [(pts[..., i, 0], pts[..., i, 1]) for i in range(4)]
+    dx1, dx2, sx = x1 - x2, x3 - x2, x0 - x1 + x2 - x3
+    dy1, dy2, sy = y1 - y2, y3 - y2, y0 - y1 + y2 - y3
+    den = dx1 * dy2 - dy1 * dx2
+    a31 = (sx * dy2 - sy * dx2) / den
+    a32 = (dx1 * sy - dy1 * sx) / den
+    r0 = torch.stack([x1 - x0 + a31 * x1, x3 - x0 + a32 * x3, x0], -1)
+    r1 = torch.stack([y1 - y0 + a31 * y1, y3 - y0 + a32 * y3, y0], -1)
+    r2 = torch.stack([a31, a32, torch.ones_like(x0)], -1)
+    return torch.stack([r0, r1, r2], -2)
+
+
+def perspective_from_points(points_src, points_dst):
+    """kornia/geometry/transform/imgwarp.py:456-462: Q(dst) @ inv3x3(Q(src)), scaled to H[2,2] = 1."""
+    h = square_to_quad(points_dst) @ inv3x3(square_to_quad(points_src))
+    return h / h[..., 2:3, 2:3]
+
+
+def crop_by_transform_mat(input_tensor, transform, out_size, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """kornia/geometry/transform/crop2d.py:340-402."""
+    t = transform.expand(input_tensor.shape[0], -1, -1).to(input_tensor)
+    if transform.shape[-2:] == (2, 3):
+        return warp_affine(input_tensor, t, out_size, mode, padding_mode, align_corners)
+    h_out, w_out = out_size
+    if not align_corners and (h_out == 1 or w_out == 1):
+        return warp_affine(input_tensor, t[:, :2, :], out_size, mode, padding_mode, align_corners)
+    if not align_corners:
+        fix = torch.tensor([[w_out / (w_out - 1.0), 0.0, -0.5], [0.0, h_out / (h_out - 1.0), -0.5], [0.0, 0.0, 1.0]]).to(t)
+        t = fix[None] @ t
+    return warp_perspective(input_tensor, t, out_size, mode, padding_mode, align_corners)
+
+
+def crop_by_boxes(input_tensor, src_box, dst_box, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """kornia/geometry/transform/crop2d.py:277-296 (output size from the destination box, bbox.py infer_bbox_shape)."""
+    t = perspective_from_points(src_box.to(input_tensor), dst_box.to(input_tensor))
+    w_out = int((dst_box[0, 1, 0] - dst_box[0, 0, 0] + 1).item())
+    h_out = int((dst_box[0, 2, 1] - dst_box[0, 0, 1] + 1).item())
+    return crop_by_transform_mat(input_tensor, t, (h_out, w_out), mode, padding_mode, align_corners)
+
+
+def _patch_corners(h, w, n, like):
+    return torch.tensor([[[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]]], device=like.device, dtype=like.dtype).expand(n, -1, -1)
+
+
+def crop_and_resize(input_tensor, boxes, size, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """kornia/geometry/transform/crop2d.py:107-122."""
+    src = boxes.to(input_tensor)
+    return crop_by_boxes(input_tensor, src, _patch_corners(size[0], size[1], src.shape[0], input_tensor), mode, padding_mode,
+                         align_corners)
+
+
+def center_crop(input_tensor, size, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """kornia/geometry/transform/crop2d.py:173-206."""
+    dst_h, dst_w = size
+    src_h, src_w = input_tensor.shape[-2:]
+    sx, sy = src_w / 2 - dst_w / 2, src_h / 2 - dst_h / 2
+    ex, ey = sx + dst_w - 1, sy + dst_h - 1
+    src = torch.tensor([[[sx, sy], [ex, sy], [ex, ey], [sx, ey]]], device=input_tensor.device, dtype=input_tensor.dtype)
+    return crop_by_boxes(input_tensor, src, _patch_corners(dst_h, dst_w, 1, input_tensor), mode, padding_mode, align_corners)
+
+
+def get_rotation_matrix2d(center, angle, scale):
+    return rotation_matrix2d(center, angle, scale)
+
+
+def get_perspective_transform(points_src, points_dst):
+    return perspective_from_points(points_src, points_dst)

@@ -51,3 +51,31 @@ def rel_l2(a, b):
     a = a.double().flatten()
     b = b.double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def run_family_case(impl, op, kwargs, ins, device=None, dtype=None):
+    """Golden cases of tests/golden/family.npz: every tensor is passed by keyword (the names are the
+    reference's parameter names), lists in ``kwargs`` become tuples.  ``*_grad`` ops return
+    dict(out=..., grad_<name>=...) for sum(out * cot)."""
+    kw = {k: _tup(v) for k, v in kwargs.items()}
+    t = {}
+    for k, v in ins.items():
+        if dtype is not None and v.is_floating_point():
+            v = v.to(dtype)
+        t[k] = v.to(device) if device is not None else v
+    fn = getattr(impl, op[:-5] if op.endswith("_grad") else op)
+    if not op.endswith("_grad"):
+        return fn(**t, **kw)
+    return t, fn, kw
+
+
+def family_grads(impl, op, kwargs, ins, outs, device=None, dtype=None):
+    t, fn, kw = run_family_case(impl, op, kwargs, ins, device, dtype)
+    wrt = [k[5:] for k in outs if k.startswith("grad_")]
+    leaves = {k: (v.clone().requires_grad_(True) if k in wrt else v) for k, v in t.items()}
+    out = fn(**leaves, **kw)
+    cot = outs["cot"].to(out)
+    grads = torch.autograd.grad((out * cot).sum(), [leaves[k] for k in wrt])
+    res = {"out": out.detach()}
+    res.update({f"grad_{k}": g for k, g in zip(wrt, grads)})
+    return res

@@ -1,0 +1,145 @@
+"""GPU parity of the callers either side of the hot path through the C ABI:
+golden vectors recorded from the reference (fp32 CPU), the oracle in fp64, and size-independent
+properties at full image sizes.  Tolerances as in test_parity_gpu.py."""
+import pytest
+import torch
+
+import kornia_b200 as K
+from conftest import golden
+from helpers import family_grads, rel_l2, run_family_case
+from oracle import kornia_restated as R
+
+pytestmark = pytest.mark.gpu
+FAM = golden("family")
+FP32 = dict(rtol=1e-4, atol=1e-5)
+DEV = "cuda"
+FWD = [n for n in FAM.names() if not FAM.meta[n]["op"].endswith("_grad")]
+GRAD = [n for n in FAM.names() if FAM.meta[n]["op"].endswith("_grad")]
+
+
+def _impl(op):
+    base = op[:-5] if op.endswith("_grad") else op
+    return K.filters if hasattr(K.filters, base) else K.geometry.transform
+
+
+def _tieflip(got, want, frac=0.02):
+    bad = (got - want).abs() > (1e-5 + 1e-4 * want.abs())
+    assert bad.float().mean().item() <= frac, f"{bad.sum().item()} / {bad.numel()} mismatches"
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_family_forward_matches_reference(name):
+    op, kw, ins, outs = FAM.case(name)
+    got = run_family_case(_impl(op), op, kw, ins, device=DEV)
+    assert got.is_cuda and got.is_contiguous() and got.dtype == outs["out"].dtype and got.shape == outs["out"].shape
+    if kw.get("mode") == "nearest":
+        _tieflip(got.cpu(), outs["out"])
+    else:
+        torch.testing.assert_close(got.cpu(), outs["out"], **FP32)
+
+
+@pytest.mark.parametrize("name", GRAD)
+def test_family_grads_match_reference(name):
+    op, kw, ins, outs = FAM.case(name)
+    got = family_grads(_impl(op), op, kw, ins, outs, device=DEV)
+    for key, want in outs.items():
+        if key != "cot":
+            assert rel_l2(got[key].cpu(), want) < 1e-4, (key, rel_l2(got[key].cpu(), want))
+
+
+@pytest.mark.parametrize("name", [n for n in FWD if FAM.meta[n]["op"] in ("spatial_gradient", "sobel", "laplacian", "box_blur")][::3])
+def test_family_filters_fp64_match_oracle(name):
+    op, kw, ins, _ = FAM.case(name)
+    got = run_family_case(K.filters, op, kw, ins, device=DEV, dtype=torch.float64)
+    want = run_family_case(R, op, kw, ins, dtype=torch.float64)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", [n for n in GRAD if FAM.meta[n]["op"] in ("spatial_gradient_grad", "sobel_grad")])
+def test_family_filter_grads_fp64_match_oracle(name):
+    op, kw, ins, outs = FAM.case(name)
+    got = family_grads(K.filters, op, kw, ins, outs, device=DEV, dtype=torch.float64)
+    want = family_grads(R, op, kw, ins, outs, dtype=torch.float64)
+    for key in want:
+        assert rel_l2(got[key].cpu(), want[key]) < 1e-11, key
+
+
+def test_spatial_gradient_gradcheck():
+    x = torch.rand(2, 2, 6, 7, device=DEV, dtype=torch.float64, requires_grad=True)
+    for mode, order in (("sobel", 1), ("diff", 2), ("sobel", 2)):
+        assert torch.autograd.gradcheck(lambda t: K.filters.spatial_gradient(t, mode, order), (x,), fast_mode=True)
+    assert torch.autograd.gradcheck(K.filters.sobel, (x,), fast_mode=True)
+
+
+def test_sobel_fused_equals_composed_path():
+    """The one-kernel magnitude (no-grad call) and the differentiable composition are the same numbers."""
+    x = torch.rand(3, 3, 67, 92, device=DEV)
+    fused = K.filters.sobel(x)
+    composed = K.filters.sobel(x.clone().requires_grad_(True)).detach()
+    torch.testing.assert_close(fused, composed, rtol=1e-6, atol=1e-7)
+    assert K._ops.launch_count > 0
+
+
+def test_spatial_gradient_unaligned_and_many_planes():
+    # storage offset of one float: the vector path must be skipped, results unchanged
+    buf = torch.rand(2 * 3 * 16 * 32 + 1, device=DEV)
+    x = buf[1:].view(2, 3, 16, 32)
+    assert x.is_contiguous() and x.data_ptr() % 16 != 0
+    torch.testing.assert_close(K.filters.spatial_gradient(x), K.filters.spatial_gradient(x.clone()), rtol=0, atol=0)
+    torch.testing.assert_close(K.filters.sobel(x), K.filters.sobel(x.clone()), rtol=0, atol=0)
+    # more planes than gridDim.z holds: the kernels loop over planes
+    many = torch.rand(70000, 1, 4, 4, device=DEV)
+    got = K.filters.spatial_gradient(many)
+    want = R.spatial_gradient(many[-9:])
+    torch.testing.assert_close(got[-9:], want, **FP32)
+    g = torch.rand_like(got)
+    leaf = many.clone().requires_grad_(True)
+    (K.filters.spatial_gradient(leaf) * g).sum().backward()
+    ref_leaf = many[-5:].clone().requires_grad_(True)
+    (R.spatial_gradient(ref_leaf) * g[-5:]).sum().backward()
+    torch.testing.assert_close(leaf.grad[-5:], ref_leaf.grad, **FP32)
+
+
+def test_full_size_properties():
+    """1080p, size-independent checks: a plane a*x + b*y + c has constant derivatives (a, b) away from
+    the border (replicate padding flattens the border itself), zero second derivatives and zero Laplacian;
+    a box blur leaves it unchanged in the interior; rotate by 0 and a unit scale are identities."""
+    H, W = 1080, 1920
+    ys, xs = torch.meshgrid(torch.arange(H, device=DEV, dtype=torch.float32), torch.arange(W, device=DEV, dtype=torch.float32),
+                            indexing="ij")
+    a, b, c = 0.25, -0.5, 3.0
+    plane = (a * xs + b * ys + c)[None, None].expand(2, 3, H, W).contiguous()
+    g = K.filters.spatial_gradient(plane, "sobel", 1, normalized=True)
+    torch.testing.assert_close(g[:, :, 0, 1:-1, 1:-1], torch.full_like(g[:, :, 0, 1:-1, 1:-1], a), rtol=0, atol=2e-4)
+    torch.testing.assert_close(g[:, :, 1, 1:-1, 1:-1], torch.full_like(g[:, :, 1, 1:-1, 1:-1], b), rtol=0, atol=2e-4)
+    g2 = K.filters.spatial_gradient(plane, "diff", 2, normalized=False)
+    assert float(g2[:, :, :, 2:-2, 2:-2].abs().max()) < 2e-3
+    mag = K.filters.sobel(plane, eps=0.0)
+    torch.testing.assert_close(mag[:, :, 1:-1, 1:-1], torch.full_like(mag[:, :, 1:-1, 1:-1], (a * a + b * b) ** 0.5), rtol=0, atol=3e-4)
+    assert float(K.filters.laplacian(plane, 5)[:, :, 2:-2, 2:-2].abs().max()) < 5e-3
+    torch.testing.assert_close(K.filters.box_blur(plane, (5, 7))[:, :, 2:-2, 3:-3], plane[:, :, 2:-2, 3:-3], rtol=1e-5, atol=1e-3)
+    noise = torch.rand(2, 3, H, W, device=DEV)
+    torch.testing.assert_close(K.geometry.transform.rotate(noise, torch.zeros(2, device=DEV)), noise, rtol=0, atol=1e-3)
+    torch.testing.assert_close(K.geometry.transform.scale(noise, torch.ones(2, 2, device=DEV)), noise, rtol=0, atol=1e-3)
+    torch.testing.assert_close(K.geometry.transform.center_crop(noise, (H - 2, W - 2)), noise[:, :, 1:-1, 1:-1], rtol=0, atol=1e-3)
+    # unsharp_mask = 2*x - blur(x): against the blur kernel itself
+    blur = K.filters.gaussian_blur2d(noise, (5, 5), (1.5, 1.5))
+    torch.testing.assert_close(K.filters.unsharp_mask(noise, (5, 5), (1.5, 1.5)), 2 * noise - blur, rtol=1e-5, atol=1e-6)
+
+
+def test_mid_size_matches_oracle_on_device():
+    """270x480 batches: CUDA path vs the oracle (the reference's torch composition) on the same device."""
+    x = torch.rand(4, 3, 270, 480, device=DEV)
+    for mode, order in (("sobel", 1), ("sobel", 2), ("diff", 1), ("diff", 2)):
+        torch.testing.assert_close(K.filters.spatial_gradient(x, mode, order), R.spatial_gradient(x, mode, order), **FP32)
+    torch.testing.assert_close(K.filters.sobel(x), R.sobel(x), **FP32)
+    torch.testing.assert_close(K.filters.box_blur(x, 5), R.box_blur(x, 5), **FP32)
+    torch.testing.assert_close(K.filters.box_blur(x, (3, 7), "replicate", True), R.box_blur(x, (3, 7), "replicate", True), **FP32)
+    torch.testing.assert_close(K.filters.laplacian(x, 7), R.laplacian(x, 7), **FP32)
+    torch.testing.assert_close(K.filters.unsharp_mask(x, (7, 7), (2.0, 2.0)), R.unsharp_mask(x, (7, 7), (2.0, 2.0)), **FP32)
+    ang = torch.tensor([10.0, -33.0, 170.0, 91.0], device=DEV)
+    smooth = torch.nn.functional.interpolate(torch.rand(4, 3, 9, 16, device=DEV), size=(270, 480), mode="bicubic", align_corners=True)
+    torch.testing.assert_close(K.geometry.transform.rotate(smooth, ang), R.rotate(smooth, ang), **FP32)
+    boxes = torch.tensor([[[10.0, 20.0], [300.0, 25.0], [310.0, 200.0], [5.0, 180.0]]], device=DEV).expand(4, 4, 2).contiguous()
+    torch.testing.assert_close(K.geometry.transform.crop_and_resize(smooth, boxes, (128, 160)), R.crop_and_resize(smooth, boxes, (128, 160)),
+                               **FP32)

@@ -1,5 +1,5 @@
 """Small workload for compute-sanitizer (memcheck / racecheck / synccheck): tiled forward (3 interpolations),
-tiled backward, tiled separable filter, at sizes with several tiles per CTA and partial edge tiles."""
+tiled backward, tiled separable filter, the derivative stencils, at sizes with several tiles per CTA and partial edge tiles."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -20,5 +20,16 @@ out = K.warp_perspective(s, m, (H, W))
 torch.autograd.grad(out.sum(), [s, m])
 K.gaussian_blur2d(src, (11, 11), (2.0, 2.0))
 K.gaussian_blur2d(src, (5, 5), (1.0, 1.0), "replicate")
+# image derivatives: odd width (scalar path), aligned width (vector path), backward, fused magnitude, 5x5 stencils
+for shape in ((2, 3, 33, 45), (1, 2, 16, 256), (2, 1, 1, 7), (3, 1, 2, 2)):
+    xg = torch.rand(*shape, generator=g).to(dev).requires_grad_(True)
+    for mode, order in (("sobel", 1), ("sobel", 2), ("diff", 2)):
+        K.filters.spatial_gradient(xg, mode, order).sum().backward()
+    K.filters.sobel(xg.detach())
+    K.filters.sobel(xg).sum().backward()
+K.filters.box_blur(src, (3, 5))
+K.filters.laplacian(src, 5)
+K.geometry.transform.rotate(src, torch.tensor([10.0, 20.0, 30.0], device=dev))
+K.geometry.transform.center_crop(src, (50, 60))
 torch.cuda.synchronize()
 print("sanitize workload done")
