@@ -124,6 +124,13 @@ int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* ker
                             int H, int W, int Bkx, int kw, int Bky, int kh, int border, int same, int dtype,
                             void* stream);
 
+/* get_perspective_transform (geometry/transform/imgwarp.py:444-462: two unit-square-to-quad maps, a closed-form
+ * 3x3 inverse, one bmm and a scale -- ~45 tiny torch launches) in one launch, for the RandomPerspective /
+ * crop_and_resize callers.  points_src, points_dst: (B,4,2) x,y corners; H_out: (B,3,3)
+ * with H[2,2] = 1.  `variant` as in kb200_warp_prelude.  No gradient: the host keeps the torch ops for that. */
+int kb200_perspective_from_points(const void* points_src, const void* points_dst, void* H_out, int B, int dtype,
+                                  int variant, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Image derivatives: spatial_gradient / sobel (filters/sobel.py:32-74,134-167:
  * F.pad(replicate) + F.conv2d with a (nout,1,k,k) weight, then for sobel two slices + 5 elementwise

@@ -442,6 +442,21 @@ int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* ker
 }
 
 
+int kb200_perspective_from_points(const void* points_src, const void* points_dst, void* H_out, int B, int dtype, int variant,
+                                  void* stream) {
+  KB_CHECK_ARG(points_src && points_dst && H_out && B > 0, "bad arguments");
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(B, 128);
+  if (dtype == KB200_F32)
+    perspective_from_points_kernel<float><<<grid, 128, 0, st>>>((const float*)points_src, (const float*)points_dst, (float*)H_out, B,
+                                                               variant);
+  else
+    perspective_from_points_kernel<double><<<grid, 128, 0, st>>>((const double*)points_src, (const double*)points_dst,
+                                                                (double*)H_out, B, variant);
+  return post_launch("perspective_from_points");
+}
+
 int kb200_spatial_gradient_forward(const void* x, const double* taps, void* out, int planes, int H, int W, int nout, int k,
                                    int magnitude, double eps, int dtype, void* stream) {
   KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);

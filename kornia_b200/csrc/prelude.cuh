@@ -120,3 +120,40 @@ __global__ void warp_prelude_backward_kernel(const T* __restrict__ m, const T* _
 }
 
 }  // namespace kb200
+
+namespace kb200 {
+
+// Unit square -> quadrilateral (Heckbert), every binary op rounded on its own like the reference's
+// chain of elementwise torch kernels (kornia/geometry/transform/imgwarp.py:411-441).
+template <typename T>
+__device__ __forceinline__ void square_to_quad(const T* __restrict__ pts, T Q[9]) {
+  using R = RN<T>;
+  const T x0 = pts[0], y0 = pts[1], x1 = pts[2], y1 = pts[3], x2 = pts[4], y2 = pts[5], x3 = pts[6], y3 = pts[7];
+  const T dx1 = R::sub(x1, x2), dx2 = R::sub(x3, x2), sx = R::sub(R::add(R::sub(x0, x1), x2), x3);
+  const T dy1 = R::sub(y1, y2), dy2 = R::sub(y3, y2), sy = R::sub(R::add(R::sub(y0, y1), y2), y3);
+  const T den = R::sub(R::mul(dx1, dy2), R::mul(dy1, dx2));
+  const T g = R::div(R::sub(R::mul(sx, dy2), R::mul(sy, dx2)), den);
+  const T h = R::div(R::sub(R::mul(dx1, sy), R::mul(dy1, sx)), den);
+  Q[0] = R::add(R::sub(x1, x0), R::mul(g, x1)); Q[1] = R::add(R::sub(x3, x0), R::mul(h, x3)); Q[2] = x0;
+  Q[3] = R::add(R::sub(y1, y0), R::mul(g, y1)); Q[4] = R::add(R::sub(y3, y0), R::mul(h, y3)); Q[5] = y0;
+  Q[6] = g; Q[7] = h; Q[8] = T(1);
+}
+
+// get_perspective_transform (imgwarp.py:456-462) in one launch: H = Q(dst) @ inverse(Q(src)), scaled to H[2,2] = 1.
+// Replaces ~45 tiny torch launches per call on the RandomPerspective / crop_and_resize path.
+template <typename T>
+__global__ void perspective_from_points_kernel(const T* __restrict__ src, const T* __restrict__ dst, T* __restrict__ out, int B,
+                                               int variant) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  T Qs[9], Qd[9], Qsi[9], Hm[9];
+  square_to_quad<T>(src + (size_t)b * 8, Qs);
+  square_to_quad<T>(dst + (size_t)b * 8, Qd);
+  inv3_torchlike<T>(Qs, Qsi, variant);
+  matmul3_torchlike<T>(Qd, Qsi, Hm, variant);
+  const T w = Hm[8];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[(size_t)b * 9 + i] = RN<T>::div(Hm[i], w);
+}
+
+}  // namespace kb200

@@ -75,14 +75,57 @@ def _unit_square_to_quad(points: torch.Tensor) -> torch.Tensor:
     return torch.stack(rows, dim=-2)
 
 
-def get_perspective_transform(points_src: torch.Tensor, points_dst: torch.Tensor) -> torch.Tensor:
-    """(B,3,3) homography taking the four ``points_src`` (B,4,2; x,y) onto ``points_dst``, scaled so
-    that H[2,2] = 1: H = Q(dst) @ Q(src)^-1 with Q the unit-square-to-quad map (imgwarp.py:444-527)."""
-    check_shape(points_src, ["B", "4", "2"])
-    check_shape(points_dst, ["B", "4", "2"])
-    check(points_src.shape == points_dst.shape, "Source data shape must match Destination data shape.")
-    check(points_src.dtype == points_dst.dtype, "Source data type must match Destination data type.")
+def _perspective_torch(points_src: torch.Tensor, points_dst: torch.Tensor) -> torch.Tensor:
     dtype = points_src.dtype
     work = dtype if dtype in (torch.float32, torch.float64) else torch.float32
     h = _unit_square_to_quad(points_dst.to(work)) @ inverse3x3(_unit_square_to_quad(points_src.to(work)))
     return (h / h[..., 2:3, 2:3]).to(dtype)
+
+
+class _FusedPerspective(torch.autograd.Function):
+    """kb200_perspective_from_points forward (one launch instead of ~45); the backward differentiates the
+    torch op sequence on the saved corner points (18 numbers per sample)."""
+
+    @staticmethod
+    def forward(ctx, points_src, points_dst):
+        from ... import _lib, _ops
+        from .._prelude import FUSED_VARIANT
+
+        ps, pd = points_src.contiguous(), points_dst.contiguous()
+        out = torch.empty((ps.shape[0], 3, 3), device=ps.device, dtype=ps.dtype)
+        with torch.cuda.device(ps.device):
+            _lib.call("kb200_perspective_from_points", ps.data_ptr(), pd.data_ptr(), out.data_ptr(), ps.shape[0],
+                      0 if ps.dtype == torch.float32 else 1, FUSED_VARIANT, torch.cuda.current_stream(ps.device).cuda_stream)
+        _ops._bump()
+        ctx.save_for_backward(ps, pd)
+        return out
+
+    @staticmethod
+    def backward(ctx, gh):
+        ps, pd = ctx.saved_tensors
+        with torch.enable_grad():
+            a = ps.detach().requires_grad_(ctx.needs_input_grad[0])
+            b = pd.detach().requires_grad_(ctx.needs_input_grad[1])
+            wrt = [t for t, need in zip((a, b), ctx.needs_input_grad) if need]
+            grads = list(torch.autograd.grad(_perspective_torch(a, b), wrt, gh)) if wrt else []
+        return tuple(grads.pop(0) if need else None for need in ctx.needs_input_grad)
+
+
+def get_perspective_transform(points_src: torch.Tensor, points_dst: torch.Tensor) -> torch.Tensor:
+    """(B,3,3) homography taking the four ``points_src`` (B,4,2; x,y) onto ``points_dst``, scaled so
+    that H[2,2] = 1: H = Q(dst) @ Q(src)^-1 with Q the unit-square-to-quad map (imgwarp.py:444-527).
+    CUDA fp32/fp64 points with batch >= 2 take one fused launch; anything else (CPU points, half
+    precision, a single sample, KORNIA_B200_TORCH_PRELUDE=1) the reference's torch op sequence."""
+    import os
+
+    from .._prelude import FUSED_MIN_BATCH
+
+    check_shape(points_src, ["B", "4", "2"])
+    check_shape(points_dst, ["B", "4", "2"])
+    check(points_src.shape == points_dst.shape, "Source data shape must match Destination data shape.")
+    check(points_src.dtype == points_dst.dtype, "Source data type must match Destination data type.")
+    fused_ok = (points_src.is_cuda and points_dst.is_cuda and points_src.dtype in (torch.float32, torch.float64)
+                and points_src.shape[0] >= FUSED_MIN_BATCH and os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") != "1")
+    if fused_ok:
+        return _FusedPerspective.apply(points_src, points_dst)
+    return _perspective_torch(points_src, points_dst)

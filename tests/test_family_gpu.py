@@ -143,3 +143,44 @@ def test_mid_size_matches_oracle_on_device():
     boxes = torch.tensor([[[10.0, 20.0], [300.0, 25.0], [310.0, 200.0], [5.0, 180.0]]], device=DEV).expand(4, 4, 2).contiguous()
     torch.testing.assert_close(K.geometry.transform.crop_and_resize(smooth, boxes, (128, 160)), R.crop_and_resize(smooth, boxes, (128, 160)),
                                **FP32)
+
+
+def _jittered_quads(B, H, W, dtype):
+    g = torch.Generator().manual_seed(7)
+    quad = torch.tensor([[0.0, 0.0], [W - 1.0, 0.0], [W - 1.0, H - 1.0], [0.0, H - 1.0]]).expand(B, 4, 2)
+    return quad.contiguous().to(DEV, dtype), (quad + 8.0 * torch.randn(B, 4, 2, generator=g)).to(DEV, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_fused_perspective_from_points_matches_torch_ops(dtype, monkeypatch):
+    """One-launch get_perspective_transform vs the reference's torch op sequence on the same device."""
+    KT = K.geometry.transform
+    src, dst = _jittered_quads(64, 1080, 1920, dtype)
+    before = K._ops.launch_count
+    fused = KT.get_perspective_transform(src, dst)
+    assert K._ops.launch_count == before + 1
+    monkeypatch.setenv("KORNIA_B200_TORCH_PRELUDE", "1")
+    plain = KT.get_perspective_transform(src, dst)
+    assert K._ops.launch_count == before + 1
+    monkeypatch.delenv("KORNIA_B200_TORCH_PRELUDE")
+    tol = dict(rtol=2e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-12, atol=1e-13)
+    torch.testing.assert_close(fused, plain, **tol)
+    torch.testing.assert_close(fused.cpu(), R.perspective_from_points(src.cpu(), dst.cpu()), rtol=1e-4, atol=1e-5)
+    print(f"fused perspective {dtype}: {(fused == plain).float().mean().item() * 100:.1f}% of entries bit-identical to the torch ops")
+    # gradients flow through the fused forward
+    a, b = src.clone().requires_grad_(True), dst.clone().requires_grad_(True)
+    cot = torch.rand(64, 3, 3, device=DEV, dtype=dtype)
+    ga, gb = torch.autograd.grad((KT.get_perspective_transform(a, b) * cot).sum(), [a, b])
+    monkeypatch.setenv("KORNIA_B200_TORCH_PRELUDE", "1")
+    a2, b2 = src.clone().requires_grad_(True), dst.clone().requires_grad_(True)
+    ga2, gb2 = torch.autograd.grad((KT.get_perspective_transform(a2, b2) * cot).sum(), [a2, b2])
+    assert rel_l2(ga, ga2) < 1e-5 and rel_l2(gb, gb2) < 1e-5
+
+
+def test_points_to_warp_pipeline_matches_oracle():
+    """The RandomPerspective data path: corner points -> homography -> warp, against the oracle's composition."""
+    src, dst = _jittered_quads(4, 270, 480, torch.float32)
+    img = torch.nn.functional.interpolate(torch.rand(4, 3, 9, 16, device=DEV), size=(270, 480), mode="bicubic", align_corners=True)
+    got = K.warp_perspective(img, K.geometry.transform.get_perspective_transform(src, dst), (270, 480), align_corners=False)
+    want = R.warp_perspective(img, R.perspective_from_points(src, dst), (270, 480), align_corners=False)
+    torch.testing.assert_close(got, want, **FP32)

@@ -63,6 +63,18 @@ with torch.no_grad():
     boxes = torch.tensor([[[100.0, 50.0], [1800.0, 60.0], [1790.0, 1000.0], [90.0, 1010.0]]], device=dev).expand(B, 4, 2).contiguous()
     line("crop_and_resize -> 1080x1920", lambda: K.geometry.transform.crop_and_resize(x, boxes, (H, W)),
          lambda: R.crop_and_resize(x, boxes, (H, W)), 8)
+    # RandomPerspective data path: corner points -> homography -> warp (one fused launch for the homography vs ~45 torch launches)
+    quad = torch.tensor([[0.0, 0.0], [W - 1.0, 0.0], [W - 1.0, H - 1.0], [0.0, H - 1.0]], device=dev).expand(B, 4, 2).contiguous()
+    quad_to = quad + 8.0 * torch.randn(B, 4, 2, device=dev)
+    KT = K.geometry.transform
+    line("points -> H -> warp_perspective", lambda: K.warp_perspective(x, KT.get_perspective_transform(quad, quad_to), (H, W)),
+         lambda: R.warp_perspective(x, R.perspective_from_points(quad, quad_to), (H, W)), 8)
+    fused_h = t(lambda: KT.get_perspective_transform(quad, quad_to), 50)
+    os.environ["KORNIA_B200_TORCH_PRELUDE"] = "1"
+    torch_h = t(lambda: KT.get_perspective_transform(quad, quad_to), 20)
+    del os.environ["KORNIA_B200_TORCH_PRELUDE"]
+    print(f"get_perspective_transform alone (B={B}): fused {fused_h * 1e3:.1f} us, torch op sequence {torch_h * 1e3:.1f} us", flush=True)
+    rows.append(dict(op="get_perspective_transform", fused_us=round(fused_h * 1e3, 1), torch_us=round(torch_h * 1e3, 1)))
 out = os.path.join(ROOT, "gpurun_out", "family_bench.json")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 json.dump(dict(B=B, shape=[B, 3, H, W], peak_gbs=peak, rows=rows), open(out, "w"), indent=1)
