@@ -150,6 +150,18 @@ int kb200_spatial_gradient_backward(const void* gout, const double* taps, void* 
                                     int nout, int k, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SSIM index map (metrics/ssim.py:92-139: five filter2d_separable calls with a Gaussian window of sigma 1.5,
+ * three product kernels and fourteen elementwise kernels) in ONE kernel: 8 B read + 4 B written per element.
+ *   img1, img2 (planes,H,W) device; taps (K,) device Gaussian window (the same for rows and columns);
+ *   out (planes,H,W) = ((2 mu1 mu2 + C1)(2 s12 + C2)) / ((mu1^2 + mu2^2 + C1)(s1 + s2 + C2) + eps),
+ *   'reflect' border, 'same' size (the 'valid' variant is a crop of it).
+ * fp32 and odd K <= 11 only: anything else returns KB200_EUNSUPPORTED and the host composes the map from
+ * kb200_sepfilter_forward (which is also the differentiable path).
+ * ------------------------------------------------------------------------------------------ */
+int kb200_ssim_forward(const void* img1, const void* img2, const void* taps, void* out, int planes, int H, int W, int K,
+                       double C1, double C2, double eps, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Diagnostics (used by tests/): counts elements where the shared-reciprocal division of the tiled
  * warp kernel differs from IEEE division in a way that could change a sampled pixel.  `count`
  * (device int, zeroed by the caller) is incremented atomically.

@@ -9,7 +9,7 @@ no CPU path and no fallback -- a missing library or a CPU tensor raises.
 """
 from __future__ import annotations
 
-from . import core, filters, geometry
+from . import core, filters, geometry, losses, metrics
 from .filters import filter2d, filter2d_separable, gaussian_blur2d
 from .geometry.transform import remap, warp_affine, warp_perspective
 
@@ -19,7 +19,8 @@ _PATCHED = {}
 
 
 def install(kornia_module=None) -> None:
-    """Rebind the hot-path functions on an imported ``kornia`` package.
+    """Rebind the hot-path functions (and the four callers that have a fused kernel of their own here:
+    ``get_perspective_transform``, ``spatial_gradient``, ``sobel``, ``ssim``) on an imported ``kornia`` package.
 
     Every module of the package that holds a reference to one of the originals is patched: the
     defining modules and re-export sites (geometry/transform/__init__.py:30, geometry/__init__.py:40,
@@ -40,6 +41,11 @@ def install(kornia_module=None) -> None:
         "filter2d": ("filters.filter", filter2d),
         "filter2d_separable": ("filters.filter", filter2d_separable),
         "gaussian_blur2d": ("filters.gaussian", gaussian_blur2d),
+        # callers with a kernel of their own here (the rest of the family reaches the kernels through the six above)
+        "get_perspective_transform": ("geometry.transform.imgwarp", geometry.transform.get_perspective_transform),
+        "spatial_gradient": ("filters.sobel", filters.spatial_gradient),
+        "sobel": ("filters.sobel", filters.sobel),
+        "ssim": ("metrics.ssim", metrics.ssim),
     }
     originals = {}
     for name, (mod, fn) in defining.items():
@@ -61,4 +67,4 @@ def uninstall() -> None:
 
 
 __all__ = ["warp_perspective", "warp_affine", "remap", "filter2d", "filter2d_separable", "gaussian_blur2d", "install",
-           "uninstall", "core", "filters", "geometry"]
+           "uninstall", "core", "filters", "geometry", "losses", "metrics"]

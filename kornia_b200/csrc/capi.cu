@@ -12,6 +12,7 @@
 #include "filter2d_tiled.cuh"
 #include "remap_tiled.cuh"
 #include "gradient.cuh"
+#include "ssim_tiled.cuh"
 
 namespace kb200 {
 
@@ -455,6 +456,21 @@ int kb200_perspective_from_points(const void* points_src, const void* points_dst
     perspective_from_points_kernel<double><<<grid, 128, 0, st>>>((const double*)points_src, (const double*)points_dst,
                                                                 (double*)H_out, B, variant);
   return post_launch("perspective_from_points");
+}
+
+int kb200_ssim_forward(const void* img1, const void* img2, const void* taps, void* out, int planes, int H, int W, int K, double C1,
+                       double C2, double eps, int dtype, void* stream) {
+  KB_CHECK_ARG(img1 && img2 && taps && out, "null pointer argument");
+  KB_CHECK_ARG(planes > 0 && H > 0 && W > 0 && K > 0, "bad sizes planes=%d H=%d W=%d K=%d", planes, H, W, K);
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  if (dtype != KB200_F32) {
+    set_error("the fused SSIM kernel is fp32 only");
+    return KB200_EUNSUPPORTED;
+  }
+  int rc = ssim_tiled_forward((const float*)img1, (const float*)img2, (const float*)taps, (float*)out, planes, H, W, K, (float)C1,
+                              (float)C2, (float)eps, (cudaStream_t)stream);
+  if (rc == KB200_EUNSUPPORTED) set_error("the fused SSIM kernel handles odd windows up to %d taps, got %d", SSIM_MAX_K, K);
+  return rc;
 }
 
 int kb200_spatial_gradient_forward(const void* x, const double* taps, void* out, int planes, int H, int W, int nout, int k,

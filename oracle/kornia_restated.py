@@ -464,3 +464,35 @@ def get_rotation_matrix2d(center, angle, scale):
 
 def get_perspective_transform(points_src, points_dst):
     return perspective_from_points(points_src, points_dst)
+
+
+# --------------------------------------------------------------------------------------
+# SSIM (five separable blurs + the index)
+# --------------------------------------------------------------------------------------
+def ssim(img1, img2, window_size, max_val=1.0, eps=1e-12, padding="same"):
+    """kornia/metrics/ssim.py:92-139: Gaussian window (sigma 1.5), blurs of x, y, x^2, y^2, x*y over a
+    reflect border, 'valid' = crop of the half-window margin."""
+    sigma = torch.tensor([[1.5]], device=img1.device, dtype=img1.dtype)
+    taps = gaussian_taps(window_size, sigma)
+    C1, C2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    k = taps.shape[-1]
+    front, rear = (k - 1) // 2, (k - 1) - (k - 1) // 2
+
+    def blur(t):
+        out = filter2d_separable(t, taps, taps)
+        return out[..., front:out.shape[-2] - rear, front:out.shape[-1] - rear] if padding == "valid" else out
+
+    mu1, mu2 = blur(img1), blur(img2)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1 ** 2, mu2 ** 2, mu1 * mu2
+    sigma1_sq = blur(img1 ** 2) - mu1_sq
+    sigma2_sq = blur(img2 ** 2) - mu2_sq
+    sigma12 = blur(img1 * img2) - mu1_mu2
+    num = (2.0 * mu1_mu2 + C1) * (2.0 * sigma12 + C2)
+    den = (mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2)
+    return num / (den + eps)
+
+
+def ssim_loss(img1, img2, window_size, max_val=1.0, eps=1e-12, reduction="mean", padding="same"):
+    """kornia/losses/ssim.py:67-82."""
+    loss = torch.clamp((1.0 - ssim(img1, img2, window_size, max_val, eps, padding)) / 2, min=0, max=1)
+    return loss.mean() if reduction == "mean" else loss.sum() if reduction == "sum" else loss

@@ -159,7 +159,10 @@ def main():
             dict(out_size=[8, 12], align_corners=ac))
     fwd("crop_mat3_shared_1px", KT.crop_by_transform_mat, "crop_by_transform_mat", dict(input_tensor=smooth, transform=hom[:1]),
         dict(out_size=[1, 12], align_corners=False))
-    grad("crop_resize_grad", KT.crop_and_resize, "crop_and_resize", dict(input_tensor=smooth, boxes=boxes), dict(size=[9, 13]), ["input_tensor", "boxes"])
+    # corners off the pixel grid: bilinear sampling is not differentiable at integer coordinates (one-sided derivatives
+    # differ), and the destination corners map exactly onto the source corners
+    soft = torch.tensor([[[1.3, 1.6], [14.2, 1.4], [14.4, 10.7], [1.1, 10.3]], [[4.3, 2.6], [30.4, 5.2], [28.7, 20.4], [3.2, 18.6]]])
+    grad("crop_resize_grad", KT.crop_and_resize, "crop_and_resize", dict(input_tensor=smooth, boxes=soft), dict(size=[9, 13]), ["input_tensor", "boxes"])
 
     bag.save(os.path.join(HERE, "family.npz"))
 

@@ -171,10 +171,14 @@ def test_install_rebinds_every_importer_of_the_reference():
             assert crop2d.warp_perspective is K.warp_perspective and crop2d.warp_affine is K.warp_affine
             assert unsharp.gaussian_blur2d is K.gaussian_blur2d
             assert aug_blur.gaussian_blur2d is K.gaussian_blur2d                 # captured by RandomGaussianBlur.__init__
+            assert aug_persp.get_perspective_transform is K.geometry.transform.get_perspective_transform
+            assert kornia.filters.sobel is K.filters.sobel and kornia.filters.spatial_gradient is K.filters.spatial_gradient
+            assert kornia.metrics.ssim is K.metrics.ssim and kornia.losses.ssim.metrics.ssim is K.metrics.ssim
             K.install(kornia)  # idempotent: the originals are remembered once
         finally:
             K.uninstall()
         assert kornia.geometry.transform.warp_perspective is orig and aug_persp.warp_perspective is orig
+        assert kornia.metrics.ssim is not K.metrics.ssim and callable(kornia.filters.sobel)
     finally:
         sys.path.remove(stub)
         sys.path.remove("/root/reference")

@@ -58,8 +58,18 @@ with torch.no_grad():
     line("box_blur 5x5 separable", lambda: K.filters.box_blur(x, 5, separable=True), lambda: R.box_blur(x, 5, separable=True), 8)
     line("laplacian 5x5", lambda: K.filters.laplacian(x, 5), lambda: R.laplacian(x, 5), 8)
     line("unsharp_mask 5x5", lambda: K.filters.unsharp_mask(x, (5, 5), (1.5, 1.5)), lambda: R.unsharp_mask(x, (5, 5), (1.5, 1.5)), 8)
+    y = (x + 0.1 * torch.randn_like(x)).clamp(0, 1)
+    line("ssim window 11 (fused, FMA bound)", lambda: K.metrics.ssim(x, y, 11), lambda: R.ssim(x, y, 11), 12)
+    line("ssim window 5", lambda: K.metrics.ssim(x, y, 5), lambda: R.ssim(x, y, 5), 12)
+    leaf = x[:8].clone().requires_grad_(True)
+    with torch.enable_grad():
+        composed = t(lambda: K.metrics.ssim(leaf, y[:8], 11), 5)
+    print(f"ssim window 11, differentiable composition (B=8): {composed:.3f} ms", flush=True)
+    del y, leaf
     ang = torch.linspace(-30, 30, B, device=dev)
-    line("rotate bilinear", lambda: K.geometry.transform.rotate(x, ang), lambda: R.rotate(x, ang), 8)
+    line("rotate +-30 deg bilinear", lambda: K.geometry.transform.rotate(x, ang), lambda: R.rotate(x, ang), 8)
+    small = torch.linspace(-4, 4, B, device=dev)
+    line("rotate +-4 deg bilinear", lambda: K.geometry.transform.rotate(x, small), lambda: R.rotate(x, small), 8)
     boxes = torch.tensor([[[100.0, 50.0], [1800.0, 60.0], [1790.0, 1000.0], [90.0, 1010.0]]], device=dev).expand(B, 4, 2).contiguous()
     line("crop_and_resize -> 1080x1920", lambda: K.geometry.transform.crop_and_resize(x, boxes, (H, W)),
          lambda: R.crop_and_resize(x, boxes, (H, W)), 8)

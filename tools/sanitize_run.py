@@ -27,6 +27,10 @@ for shape in ((2, 3, 33, 45), (1, 2, 16, 256), (2, 1, 1, 7), (3, 1, 2, 2)):
         K.filters.spatial_gradient(xg, mode, order).sum().backward()
     K.filters.sobel(xg.detach())
     K.filters.sobel(xg).sum().backward()
+for ws in (3, 7, 11):
+    K.metrics.ssim(src, src.flip(-1).contiguous(), ws)
+odd = torch.rand(2, 1, 45, 67, generator=g).to(dev)
+K.metrics.ssim(odd, odd.flip(-2).contiguous(), 5, padding="valid")
 K.filters.box_blur(src, (3, 5))
 K.filters.laplacian(src, 5)
 K.geometry.transform.rotate(src, torch.tensor([10.0, 20.0, 30.0], device=dev))
