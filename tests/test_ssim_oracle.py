@@ -22,7 +22,9 @@ def test_oracle_ssim_matches_reference(name):
             if key != "cot":
                 assert rel_l2(got[key], want) < 2e-6, key
     else:
-        torch.testing.assert_close(run_family_case(R, op, kw, ins), outs["out"], rtol=1e-5, atol=1e-6)
+        got = run_family_case(R, op, kw, ins)
+        # reduced losses are 0-d; the .npz writer stores them as one-element arrays
+        torch.testing.assert_close(got, outs["out"].reshape(got.shape), rtol=1e-5, atol=1e-6)
 
 
 def test_ssim_contract():
