@@ -3,6 +3,8 @@
 
 namespace kb200 {
 
+constexpr long long SQUARE_MIN_PIXELS = 1ll << 20;  // below this the second launch costs more than it can save
+
 // Returns KB200_EUNSUPPORTED when the request is outside this kernel's envelope (the caller then uses
 // warp_fwd_generic): C > 4 (C > 1 and != 3 for nearest / bicubic / fill), rows not 16-byte aligned.
 int warp_tma_forward(const float* src, const float* m, const float* bx, const float* by, const float* fill, float* out, int B, int C,
@@ -11,7 +13,19 @@ int warp_tma_forward(const float* src, const float* m, const float* bx, const fl
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0) return KB200_EUNSUPPORTED;
   if ((long long)B * C > 0x7fffffffll || (long long)B * ((h + 31) / 32) > 0x7fffffffll) return KB200_EUNSUPPORTED;
   if (pad == KB200_FILL && !fill) return KB200_EUNSUPPORTED;
-  const TmaFwdArgs a{src, m, bx, by, fill, out, B, C, H, W, h, w, Bm, projective, pad, align};
+  TmaFwdArgs a{src, m, bx, by, fill, out, B, C, H, W, h, w, Bm, projective, pad, align, 0};
+  if (interp == KB200_BILINEAR && (C == 1 || C == 3) && (long long)B * h * w >= SQUARE_MIN_PIXELS && !tma_cfg_env_set()) {
+    // Two footprint classes, two tile shapes (warp_tma_square.cu).  Small problems stay on one launch: they are
+    // launch-latency bound and every tile that does not fit is still exact.  KB200_DISABLE_SQUARE_TILES=1 restores
+    // the single-kernel behaviour (tests compare the two bit for bit).
+    const char* off = getenv("KB200_DISABLE_SQUARE_TILES");
+    if (!(off && off[0] == '1')) {
+      a.only_class = CLASS_SQUARE;
+      const int rc = warp_tma_forward_square(a, st);
+      if (rc != KB200_OK && rc != KB200_EUNSUPPORTED) return rc;
+      a.only_class = rc == KB200_OK ? CLASS_WIDE : 0;
+    }
+  }
   switch (interp) {
     case KB200_BILINEAR: return warp_tma_forward_bilinear(a, st);
     case KB200_NEAREST: return warp_tma_forward_nearest(a, st);

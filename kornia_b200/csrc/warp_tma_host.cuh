@@ -30,6 +30,11 @@ static int launch_warp_tma_cfg(const CUtensorMap& map, const TmaWarpParams& p, i
   return KB200_OK;
 }
 
+inline bool tma_cfg_env_set() {
+  const char* e = getenv("KB200_TMA_CFG");
+  return e && e[0];
+}
+
 // Tuning knob for experiments (RGB / zeros only): KB200_TMA_CFG="TWxTHxBWxBHxSTAGESxCTAS[xL2PROMO]"
 inline TmaCfg tma_cfg(int C, int pad) {
   TmaCfg c = TMA_CFG_DEFAULT;
@@ -67,6 +72,7 @@ struct TmaFwdArgs {
   const float *src, *m, *bx, *by, *fill;
   float* out;
   int B, C, H, W, h, w, Bm, projective, pad, align;
+  int only_class;  // 0: all samples; CLASS_WIDE / CLASS_SQUARE: only the samples of that footprint class
 };
 
 template <int INTERP>
@@ -89,7 +95,7 @@ static int warp_tma_forward_impl(const TmaFwdArgs& a, cudaStream_t st) {
   if (cr != CUDA_SUCCESS) return KB200_EUNSUPPORTED;
   const char* co = getenv("KB200_TMA_COPYONLY");
   TmaWarpParams p{a.src, a.m, a.bx, a.by, a.fill, a.out, a.B, a.H, a.W, a.h, a.w, a.Bm, a.align,
-                  (INTERP == KB200_BILINEAR && co && co[0] == '1') ? 1 : 0};
+                  (INTERP == KB200_BILINEAR && co && co[0] == '1') ? 1 : 0, a.only_class};
   const int C = a.C, pad = a.pad;
   const bool projective = a.projective != 0, align = a.align != 0;
 #define KB_TMA_CASE(NC_, PAD_)                                                                                                   \
@@ -121,5 +127,7 @@ static int warp_tma_forward_impl(const TmaFwdArgs& a, cudaStream_t st) {
 int warp_tma_forward_bilinear(const TmaFwdArgs& a, cudaStream_t st);
 int warp_tma_forward_nearest(const TmaFwdArgs& a, cudaStream_t st);
 int warp_tma_forward_bicubic(const TmaFwdArgs& a, cudaStream_t st);
+// bilinear, C in {1,3}: 32 x 32 output tiles with a 56 x 56 source box, for the samples of class CLASS_SQUARE
+int warp_tma_forward_square(const TmaFwdArgs& a, cudaStream_t st);
 
 }  // namespace kb200

@@ -53,7 +53,9 @@ def test_family_filters_fp64_match_oracle(name):
     op, kw, ins, _ = FAM.case(name)
     got = run_family_case(K.filters, op, kw, ins, device=DEV, dtype=torch.float64)
     want = run_family_case(R, op, kw, ins, dtype=torch.float64)
-    torch.testing.assert_close(got.cpu(), want, rtol=1e-11, atol=1e-12)
+    # fp64-grade agreement (four orders beyond fp32); the host BLAS behind the oracle's fp64 convolution differs from
+    # box to box at the 1e-11 level (observed), hence not tighter
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-9, atol=1e-10)
 
 
 @pytest.mark.parametrize("name", [n for n in GRAD if FAM.meta[n]["op"] in ("spatial_gradient_grad", "sobel_grad")])
