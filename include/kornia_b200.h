@@ -48,6 +48,9 @@ const char* kb200_last_error(void);
 /* Name of the device-code variant the last kb200_warp_forward call on this thread dispatched to
  * ("tma_tile" or "generic"); for tests and the bench. */
 const char* kb200_last_warp_variant(void);
+/* Kernels that call launched: 1, or 2 when the tiled path ran both tile shapes (64x32 tiles for near-identity
+ * samples, 32x32 tiles for rotated / sheared ones; each kernel skips the other's samples). */
+int kb200_last_warp_launches(void);
 
 /* ------------------------------------------------------------------------------------------
  * Fused projective / affine warp, forward.

@@ -30,6 +30,7 @@ SIGNATURES = {
     "kb200_abi_version": (_i, []),
     "kb200_last_error": (ctypes.c_char_p, []),
     "kb200_last_warp_variant": (ctypes.c_char_p, []),
+    "kb200_last_warp_launches": (_i, []),
     "kb200_warp_forward": (_i, [_vp] * 6 + [_i] * 12 + [_vp]),
     "kb200_warp_prelude": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),
     "kb200_warp_prelude_backward": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
@@ -106,3 +107,7 @@ def call(name: str, *args) -> None:
 
 def last_warp_variant() -> str:
     return load().kb200_last_warp_variant().decode()
+
+
+def last_warp_launches() -> int:
+    return int(load().kb200_last_warp_launches())

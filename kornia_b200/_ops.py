@@ -92,7 +92,7 @@ class WarpFunction(torch.autograd.Function):
             with torch.cuda.device(src.device), _Timed("warp_forward", src):
                 _lib.call("kb200_warp_forward", _ptr(src_c), _ptr(m_c), _ptr(bx), _ptr(by), _ptr(fill_c), _ptr(out),
                           B, C, H, W, h, w, m_c.shape[0], int(projective), interp, pad, int(align), dt, _stream(src))
-            _bump()
+            _bump(_lib.last_warp_launches())
         else:
             out.zero_()
         ctx.save_for_backward(src_c, m_c, bx, by, fill_c if fill_c is not None else torch.empty(0, device=src.device))

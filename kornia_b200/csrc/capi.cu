@@ -18,6 +18,7 @@ namespace kb200 {
 
 static thread_local char g_err[512] = "";
 static thread_local const char* g_variant = "none";
+static thread_local int g_warp_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -159,6 +160,7 @@ using namespace kb200;
 int kb200_abi_version(void) { return KB200_ABI_VERSION; }
 const char* kb200_last_error(void) { return g_err; }
 const char* kb200_last_warp_variant(void) { return g_variant; }
+int kb200_last_warp_launches(void) { return g_warp_launches; }
 
 int kb200_warp_forward(const void* src, const void* m, const void* bx, const void* by, const void* fill, void* out, int B,
                        int C, int H, int W, int h, int w, int Bm, int projective, int interp, int pad, int align_corners,
@@ -176,12 +178,15 @@ int kb200_warp_forward(const void* src, const void* m, const void* bx, const voi
                           (float*)out, B, C, H, W, h, w, Bm, projective, interp, pad, align_corners, st);
     if (rc != KB200_EUNSUPPORTED) {
       g_variant = "tma_tile";
+      g_warp_launches = warp_tma_last_launches();
       return rc;
     }
     g_variant = "generic";
+    g_warp_launches = 1;
     return warp_forward_t<float>(src, m, bx, by, fill, out, B, C, H, W, h, w, Bm, projective, interp, pad, align_corners, st);
   }
   g_variant = "generic";
+  g_warp_launches = 1;
   return warp_forward_t<double>(src, m, bx, by, fill, out, B, C, H, W, h, w, Bm, projective, interp, pad, align_corners, st);
 }
 

@@ -3,6 +3,9 @@
 
 namespace kb200 {
 
+static thread_local int g_tma_launches = 1;
+int warp_tma_last_launches() { return g_tma_launches; }
+
 constexpr long long SQUARE_MIN_PIXELS = 1ll << 20;  // below this the second launch costs more than it can save
 
 // Returns KB200_EUNSUPPORTED when the request is outside this kernel's envelope (the caller then uses
@@ -14,6 +17,7 @@ int warp_tma_forward(const float* src, const float* m, const float* bx, const fl
   if ((long long)B * C > 0x7fffffffll || (long long)B * ((h + 31) / 32) > 0x7fffffffll) return KB200_EUNSUPPORTED;
   if (pad == KB200_FILL && !fill) return KB200_EUNSUPPORTED;
   TmaFwdArgs a{src, m, bx, by, fill, out, B, C, H, W, h, w, Bm, projective, pad, align, 0};
+  g_tma_launches = 1;
   if (interp == KB200_BILINEAR && (C == 1 || C == 3) && (long long)B * h * w >= SQUARE_MIN_PIXELS && !tma_cfg_env_set()) {
     // Two footprint classes, two tile shapes (warp_tma_square.cu).  Small problems stay on one launch: they are
     // launch-latency bound and every tile that does not fit is still exact.  KB200_DISABLE_SQUARE_TILES=1 restores
@@ -24,6 +28,7 @@ int warp_tma_forward(const float* src, const float* m, const float* bx, const fl
       const int rc = warp_tma_forward_square(a, st);
       if (rc != KB200_OK && rc != KB200_EUNSUPPORTED) return rc;
       a.only_class = rc == KB200_OK ? CLASS_WIDE : 0;
+      if (rc == KB200_OK) g_tma_launches = 2;
     }
   }
   switch (interp) {
