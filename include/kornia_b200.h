@@ -127,12 +127,26 @@ int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* ker
                             int H, int W, int Bkx, int kw, int Bky, int kh, int border, int same, int dtype,
                             void* stream);
 
+/* unsharp_mask (filters/unsharp.py:53-54): out = lerp(filter2d_separable(x), x, weight), the blend done in the epilogue
+ * of the one-pass separable kernel instead of a separate pass over three full-size tensors.  Same arguments as
+ * kb200_sepfilter_forward plus `weight` (torch.lerp semantics).  fp32, square odd kernels up to 11 taps,
+ * constant / reflect / replicate, 'same': anything else returns KB200_EUNSUPPORTED (the host then blends with torch). */
+int kb200_sepfilter_lerp_forward(const void* x, const void* kernel_x, const void* kernel_y, void* out, int B, int C, int H,
+                                 int W, int Bkx, int kw, int Bky, int kh, int border, int same, double weight, int dtype,
+                                 void* stream);
+
 /* get_perspective_transform (geometry/transform/imgwarp.py:444-462: two unit-square-to-quad maps, a closed-form
  * 3x3 inverse, one bmm and a scale -- ~45 tiny torch launches) in one launch, for the RandomPerspective /
  * crop_and_resize callers.  points_src, points_dst: (B,4,2) x,y corners; H_out: (B,3,3)
  * with H[2,2] = 1.  `variant` as in kb200_warp_prelude.  No gradient: the host keeps the torch ops for that. */
 int kb200_perspective_from_points(const void* points_src, const void* points_dst, void* H_out, int B, int dtype,
                                   int variant, void* stream);
+
+/* get_rotation_matrix2d (geometry/transform/imgwarp.py:529-622: four eye_like, index assignments, deg2rad, cos, sin,
+ * stack and three bmm -- ~35 tiny torch launches) in one launch, for rotate / scale / RandomAffine (SURVEY.md 8f rows
+ * 1-2).  center (B,2) x,y; angle (B,) degrees; scale (B,2); M_out (B,2,3) = T(c) R S T(-c).  No gradient. */
+int kb200_rotation_matrix2d(const void* center, const void* angle, const void* scale, void* M_out, int B, int dtype,
+                            int variant, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Image derivatives: spatial_gradient / sobel (filters/sobel.py:32-74,134-167:

@@ -43,10 +43,12 @@ SIGNATURES = {
     "kb200_filter2d_backward_kernel_workspace_bytes": (_sz, [_i] * 8),
     "kb200_filter2d_backward_kernel": (_i, [_vp] * 4 + [_i] * 10 + [_vp]),
     "kb200_sepfilter_forward": (_i, [_vp] * 4 + [_i] * 11 + [_vp]),
+    "kb200_rotation_matrix2d": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "kb200_perspective_from_points": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "kb200_ssim_forward": (_i, [_vp] * 4 + [_i] * 4 + [ctypes.c_double] * 3 + [_i, _vp]),
     "kb200_spatial_gradient_forward": (_i, [_vp, _vp, _vp] + [_i] * 6 + [ctypes.c_double, _i, _vp]),
     "kb200_spatial_gradient_backward": (_i, [_vp, _vp, _vp] + [_i] * 6 + [_vp]),
+    "kb200_sepfilter_lerp_forward": (_i, [_vp] * 4 + [_i] * 10 + [ctypes.c_double, _i, _vp]),
     "kb200_debug_fastdiv_mismatches": (_i, [_vp, _vp, _i, _vp, _vp]),
 }
 

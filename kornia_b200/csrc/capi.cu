@@ -478,6 +478,21 @@ int kb200_ssim_forward(const void* img1, const void* img2, const void* taps, voi
   return rc;
 }
 
+int kb200_rotation_matrix2d(const void* center, const void* angle, const void* scale, void* M_out, int B, int dtype, int variant,
+                            void* stream) {
+  KB_CHECK_ARG(center && angle && scale && M_out && B > 0, "bad arguments");
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(B, 128);
+  if (dtype == KB200_F32)
+    rotation_matrix2d_kernel<float><<<grid, 128, 0, st>>>((const float*)center, (const float*)angle, (const float*)scale, (float*)M_out, B,
+                                                         variant);
+  else
+    rotation_matrix2d_kernel<double><<<grid, 128, 0, st>>>((const double*)center, (const double*)angle, (const double*)scale,
+                                                          (double*)M_out, B, variant);
+  return post_launch("rotation_matrix2d");
+}
+
 int kb200_spatial_gradient_forward(const void* x, const double* taps, void* out, int planes, int H, int W, int nout, int k,
                                    int magnitude, double eps, int dtype, void* stream) {
   KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
@@ -488,6 +503,23 @@ int kb200_spatial_gradient_backward(const void* gout, const double* taps, void* 
                                     int dtype, void* stream) {
   KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
   return spatial_gradient_backward(gout, taps, gx, planes, H, W, nout, k, dtype, (cudaStream_t)stream);
+}
+
+int kb200_sepfilter_lerp_forward(const void* x, const void* kernel_x, const void* kernel_y, void* out, int B, int C, int H, int W,
+                                 int Bkx, int kw, int Bky, int kh, int border, int same, double weight, int dtype, void* stream) {
+  int rc = check_filter(x, kernel_x, B, C, H, W, Bkx, kh, kw, border, same, dtype);
+  if (rc) return rc;
+  KB_CHECK_ARG(kernel_y && out, "null pointer argument");
+  KB_CHECK_ARG(Bky > 0 && B % Bky == 0, "kernel_y batch %d must divide the input batch %d", Bky, B);
+  if (dtype != KB200_F32 || (long long)B * C > MAX_Z) {
+    set_error("the fused filter + lerp kernel is fp32 only");
+    return KB200_EUNSUPPORTED;
+  }
+  const float w = (float)weight;
+  rc = sepfilter_tiled_forward((const float*)x, (const float*)kernel_x, (const float*)kernel_y, (float*)out, B, C, H, W, Bkx, kw, Bky,
+                               kh, border, same, (cudaStream_t)stream, &w);
+  if (rc == KB200_EUNSUPPORTED) set_error("the fused filter + lerp kernel covers square odd kernels up to 11 taps, 'same', non-circular borders");
+  return rc;
 }
 
 int kb200_warp_prelude(const void* M, void* m_out, int B, int rows, int H, int W, int h, int w, int dtype, int variant,

@@ -157,3 +157,36 @@ __global__ void perspective_from_points_kernel(const T* __restrict__ src, const 
 }
 
 }  // namespace kb200
+
+namespace kb200 {
+
+__device__ __forceinline__ float cos_t(float v) { return cosf(v); }
+__device__ __forceinline__ double cos_t(double v) { return cos(v); }
+__device__ __forceinline__ float sin_t(float v) { return sinf(v); }
+__device__ __forceinline__ double sin_t(double v) { return sin(v); }
+
+// get_rotation_matrix2d (imgwarp.py:607-622) in one launch: T(c) @ R(angle) @ S(scale) @ T(-c), the three 3x3
+// products accumulated like torch's batched GEMM, the angle converted like deg2rad (conversions.py:148: times the
+// fp32 constant pi, divided by 180).  Replaces ~35 tiny torch launches on the rotate / scale / RandomAffine path.
+template <typename T>
+__global__ void rotation_matrix2d_kernel(const T* __restrict__ center, const T* __restrict__ angle, const T* __restrict__ scale,
+                                         T* __restrict__ out, int B, int variant) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  using R = RN<T>;
+  const T cx = center[2 * b], cy = center[2 * b + 1];
+  const T rad = R::div(R::mul(angle[b], (T)3.14159265358979323846f), (T)180.0);
+  const T c = cos_t(rad), s = sin_t(rad);
+  const T to_c[9] = {T(1), T(0), cx, T(0), T(1), cy, T(0), T(0), T(1)};
+  const T from_c[9] = {T(1), T(0), -cx, T(0), T(1), -cy, T(0), T(0), T(1)};
+  const T rot[9] = {c, s, T(0), -s, c, T(0), T(0), T(0), T(1)};
+  const T scl[9] = {R::mul(T(1), scale[2 * b]), T(0), T(0), T(0), R::mul(T(1), scale[2 * b + 1]), T(0), T(0), T(0), T(1)};
+  T a[9], ab[9], abc[9];
+  matmul3_torchlike<T>(to_c, rot, a, variant);
+  matmul3_torchlike<T>(a, scl, ab, variant);
+  matmul3_torchlike<T>(ab, from_c, abc, variant);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) out[(size_t)b * 6 + i] = abc[i];
+}
+
+}  // namespace kb200

@@ -3,11 +3,11 @@
 
 namespace kb200 {
 
-template <int K, int BORDER>
+template <int K, int BORDER, bool LERP = false>
 static int launch_sep_tiled(const CUtensorMap& map, const SepTiledParams& p, cudaStream_t st) {
   constexpr int BH = SEPT_TH + K - 1;
   constexpr size_t smem = (size_t)(2 * BH * SEPT_BW + BH * SEPT_TW) * 4 + 2 * sizeof(uint64_t);
-  auto kern = sepfilter_tiled_kernel<K, BORDER>;
+  auto kern = sepfilter_tiled_kernel<K, BORDER, LERP>;
   static unsigned long long configured = 0;  // per instantiation, one bit per device
   if (first_use_on_device(configured)) {
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -27,7 +27,7 @@ static int launch_sep_tiled(const CUtensorMap& map, const SepTiledParams& p, cud
 // KB200_EUNSUPPORTED -> caller uses sepfilter_fwd_generic (circular border, 'valid', even / non-square /
 // > 17-tap kernels, rows not 16-byte aligned, images narrower than the fold distance).
 int sepfilter_tiled_forward(const float* x, const float* kx, const float* ky, float* out, int B, int C, int H, int W,
-                                   int Bkx, int kw, int Bky, int kh, int border, int same, cudaStream_t st) {
+                                   int Bkx, int kw, int Bky, int kh, int border, int same, cudaStream_t st, const float* lerp_w) {
   const char* off = getenv("KB200_DISABLE_TILED_FILTER");
   if (off && off[0] == '1') return KB200_EUNSUPPORTED;
   if (!same || kw != kh || (kw & 1) == 0 || kw < 3 || kw > 17 || border == KB200_CIRCULAR) return KB200_EUNSUPPORTED;
@@ -46,7 +46,23 @@ int sepfilter_tiled_forward(const float* x, const float* kx, const float* ky, fl
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return KB200_EUNSUPPORTED;
-  SepTiledParams p{kx, ky, out, C, H, W, Bkx, Bky, B * C};
+  SepTiledParams p{kx, ky, out, C, H, W, Bkx, Bky, B * C, x, lerp_w ? *lerp_w : 0.f};
+  if (lerp_w) {
+    if (kw > 11 || (reinterpret_cast<uintptr_t>(x) & 7) != 0) return KB200_EUNSUPPORTED;
+#define KB_SEP_LERP_CASE(K_)                                                                     \
+  if (kw == K_) {                                                                                \
+    if (border == KB200_CONSTANT) return launch_sep_tiled<K_, KB200_CONSTANT, true>(map, p, st); \
+    if (border == KB200_REFLECT) return launch_sep_tiled<K_, KB200_REFLECT, true>(map, p, st);   \
+    return launch_sep_tiled<K_, KB200_REPLICATE, true>(map, p, st);                              \
+  }
+    KB_SEP_LERP_CASE(3)
+    KB_SEP_LERP_CASE(5)
+    KB_SEP_LERP_CASE(7)
+    KB_SEP_LERP_CASE(9)
+    KB_SEP_LERP_CASE(11)
+#undef KB_SEP_LERP_CASE
+    return KB200_EUNSUPPORTED;
+  }
 #define KB_SEP_CASE(K_)                                                                    \
   if (kw == K_) {                                                                          \
     if (border == KB200_CONSTANT) return launch_sep_tiled<K_, KB200_CONSTANT>(map, p, st); \

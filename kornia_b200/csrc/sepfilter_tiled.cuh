@@ -37,9 +37,21 @@ struct SepTiledParams {
   const float* ky;  // (Bky, K)
   float* out;
   int C, H, W, Bkx, Bky, planes;
+  const float* x;   // LERP only: the input again (the epilogue re-reads the centre texels, an L2 hit)
+  float lerp_w;     // LERP only: out = lerp(filtered, x, lerp_w)
 };
 
-template <int K, int BORDER>
+// torch.lerp(start, end, w) as ATen evaluates it (ATen/native/Lerp.h): start + w * (end - start) for |w| < 0.5,
+// end - (end - start) * (1 - w) otherwise; products feeding an add may contract to an FMA there, as here.
+__device__ __forceinline__ float lerp_like_torch(float start, float end, float w) {
+  const float diff = __fsub_rn(end, start);
+  return fabsf(w) < 0.5f ? fmaf(w, diff, start) : fmaf(-diff, __fsub_rn(1.f, w), end);
+}
+
+// LERP: the epilogue blends the filtered value with the input, out = lerp(filtered, x, w) -- unsharp_mask
+// (filters/unsharp.py:53-54: gaussian_blur2d, then a separate torch.lerp pass over three full-size tensors) in the
+// blur's own pass.
+template <int K, int BORDER, bool LERP = false>
 __global__ void __launch_bounds__(256, 3) sepfilter_tiled_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                  const __grid_constant__ SepTiledParams p) {
   constexpr int HALO = (K - 1) / 2;
@@ -186,6 +198,16 @@ __global__ void __launch_bounds__(256, 3) sepfilter_tiled_kernel(const __grid_co
             if (i - o >= 0 && i - o < K) acc[o] = __ffma2_rn(ky2[i - o], v, acc[o]);
           }
         }
+        if (LERP) {
+          const float* xin = p.x + (orow - p.out);
+#pragma unroll
+          for (int o = 0; o < RY; ++o) {
+            if (y0 + yb * RY + o < p.H && tx * TW + 2 * cp < p.W) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(xin + (size_t)o * p.W));
+              acc[o] = make_float2(lerp_like_torch(acc[o].x, v.x, p.lerp_w), lerp_like_torch(acc[o].y, v.y, p.lerp_w));
+            }
+          }
+        }
         if (rows_full && (tx + 1) * TW <= p.W) {
           float* op = orow;
 #pragma unroll
@@ -205,7 +227,8 @@ __global__ void __launch_bounds__(256, 3) sepfilter_tiled_kernel(const __grid_co
   }
 }
 
+// lerp_w == nullptr: plain filter; otherwise out = lerp(filtered, x, *lerp_w) (odd K <= 11 only)
 int sepfilter_tiled_forward(const float* x, const float* kx, const float* ky, float* out, int B, int C, int H, int W, int Bkx, int kw,
-                            int Bky, int kh, int border, int same, cudaStream_t st);
+                            int Bky, int kh, int border, int same, cudaStream_t st, const float* lerp_w = nullptr);
 
 }  // namespace kb200

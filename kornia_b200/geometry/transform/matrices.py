@@ -30,6 +30,32 @@ def _eye3(like: torch.Tensor) -> torch.Tensor:
     return torch.eye(3, device=like.device, dtype=like.dtype)[None].repeat(like.shape[0], 1, 1)
 
 
+def _fused_ok(*tensors: torch.Tensor) -> bool:
+    """One-launch builders apply to CUDA fp32/fp64 inputs with batch >= 2 that need no gradient (torch's batched GEMM
+    takes another path for a single sample; autograd keeps the torch op sequence)."""
+    import os
+
+    from .._prelude import FUSED_MIN_BATCH
+
+    t0 = tensors[0]
+    return (all(t.is_cuda for t in tensors) and t0.dtype in (torch.float32, torch.float64) and t0.shape[0] >= FUSED_MIN_BATCH
+            and not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors))
+            and os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") != "1")
+
+
+def _fused_rotation(center: torch.Tensor, angle: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    from ... import _lib, _ops
+    from .._prelude import FUSED_VARIANT
+
+    c, a, s = center.contiguous(), angle.contiguous(), scale.contiguous()
+    out = torch.empty((c.shape[0], 2, 3), device=c.device, dtype=c.dtype)
+    with torch.cuda.device(c.device):
+        _lib.call("kb200_rotation_matrix2d", c.data_ptr(), a.data_ptr(), s.data_ptr(), out.data_ptr(), c.shape[0],
+                  0 if c.dtype == torch.float32 else 1, FUSED_VARIANT, torch.cuda.current_stream(c.device).cuda_stream)
+    _ops._bump()
+    return out
+
+
 def get_rotation_matrix2d(center: torch.Tensor, angle: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """(B,2,3) rotation by ``angle`` degrees (counter-clockwise on screen) and per-axis ``scale``
     about ``center`` (x, y): T(c) @ R @ S @ T(-c)."""
@@ -48,6 +74,8 @@ def get_rotation_matrix2d(center: torch.Tensor, angle: torch.Tensor, scale: torc
     if not (center.device == angle.device == scale.device) or not (center.dtype == angle.dtype == scale.dtype):
         raise ValueError(f"Inputs must have same device Got center ({center.device}, {center.dtype}), angle ({angle.device}, "
                          f"{angle.dtype}) and scale ({scale.device}, {scale.dtype})")
+    if _fused_ok(center, angle, scale):
+        return _fused_rotation(center, angle, scale)
     to_center, from_center, scaling, rotation = _eye3(center), _eye3(center), _eye3(center), _eye3(center)
     to_center[:, :2, 2] = center
     from_center[:, :2, 2] = -center

@@ -187,3 +187,51 @@ def test_points_to_warp_pipeline_matches_oracle():
     got = K.warp_perspective(img, K.geometry.transform.get_perspective_transform(src, dst), (270, 480), align_corners=False)
     want = R.warp_perspective(img, R.perspective_from_points(src, dst), (270, 480), align_corners=False)
     torch.testing.assert_close(got, want, **FP32)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_fused_rotation_matrix_matches_torch_ops(dtype, monkeypatch):
+    """One-launch get_rotation_matrix2d vs the reference's torch op sequence on the same device, and through rotate()."""
+    KT = K.geometry.transform
+    g = torch.Generator().manual_seed(11)
+    center = (torch.rand(64, 2, generator=g) * 1000).to(DEV, dtype)
+    angle = ((torch.rand(64, generator=g) - 0.5) * 720).to(DEV, dtype)
+    scale = (0.5 + torch.rand(64, 2, generator=g)).to(DEV, dtype)
+    before = K._ops.launch_count
+    fused = KT.get_rotation_matrix2d(center, angle, scale)
+    assert K._ops.launch_count == before + 1 and fused.shape == (64, 2, 3)
+    monkeypatch.setenv("KORNIA_B200_TORCH_PRELUDE", "1")
+    plain = KT.get_rotation_matrix2d(center, angle, scale)
+    assert K._ops.launch_count == before + 1
+    monkeypatch.delenv("KORNIA_B200_TORCH_PRELUDE")
+    tol = dict(rtol=1e-5, atol=2e-4) if dtype == torch.float32 else dict(rtol=1e-12, atol=1e-10)  # translations reach ~1e3
+    torch.testing.assert_close(fused, plain, **tol)
+    torch.testing.assert_close(fused.cpu(), R.rotation_matrix2d(center.cpu(), angle.cpu(), scale.cpu()), rtol=1e-4, atol=1e-3)
+    print(f"fused rotation matrix {dtype}: {(fused == plain).float().mean().item() * 100:.1f}% of entries bit-identical to the torch ops")
+    # a center that requires grad keeps the differentiable torch path
+    leaf = center.clone().requires_grad_(True)
+    KT.get_rotation_matrix2d(leaf, angle, scale).sum().backward()
+    assert leaf.grad is not None and K._ops.launch_count == before + 1
+    img = torch.rand(8, 3, 96, 128, device=DEV, dtype=dtype)
+    ang8 = angle[:8]
+    fused_img = KT.rotate(img, ang8)
+    monkeypatch.setenv("KORNIA_B200_TORCH_PRELUDE", "1")
+    torch.testing.assert_close(fused_img, KT.rotate(img, ang8), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("ks,border", [(3, "reflect"), (5, "replicate"), (7, "constant"), (11, "reflect")])
+def test_fused_unsharp_equals_blur_then_lerp(ks, border):
+    """unsharp_mask in the blur kernel's epilogue vs blur + torch.lerp (the reference's two steps) on the same device."""
+    x = torch.rand(3, 3, 131, 260, device=DEV)
+    before = K._ops.launch_count
+    fused = K.filters.unsharp_mask(x, (ks, ks), (1.3, 1.7), border)
+    assert K._ops.launch_count == before + 1, "one kernel"
+    two_step = torch.lerp(K.filters.gaussian_blur2d(x, (ks, ks), (1.3, 1.7), border), x, weight=2.0)
+    torch.testing.assert_close(fused, two_step, rtol=1e-6, atol=1e-6)
+    print(f"unsharp k={ks}: {(fused == two_step).float().mean().item() * 100:.2f}% bit-identical to blur + torch.lerp")
+    torch.testing.assert_close(fused, R.unsharp_mask(x, (ks, ks), (1.3, 1.7), border), **FP32)
+    # outside the fused envelope (non-square kernel, gradient needed): the composition
+    torch.testing.assert_close(K.filters.unsharp_mask(x, (3, 5), (1.0, 1.0)), R.unsharp_mask(x, (3, 5), (1.0, 1.0)), **FP32)
+    leaf = x.clone().requires_grad_(True)
+    K.filters.unsharp_mask(leaf, (ks, ks), (1.3, 1.7), border).sum().backward()
+    assert leaf.grad is not None
