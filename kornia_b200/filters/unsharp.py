@@ -24,36 +24,49 @@ def unsharp_mask(input: torch.Tensor, kernel_size: tuple[int, int] | int, sigma:
     return torch.lerp(blurred, input, weight=2.0)
 
 
-def _fused_unsharp(input, kernel_size, sigma, border_type):
-    """The blur's validation and taps, then kb200_sepfilter_lerp_forward; None when the request is outside the fused
-    kernel's envelope (the caller composes)."""
-    from .. import _lib, _ops
-    from . import gaussian as G
+def _fused_request(input, kernel_size, sigma, border_type):
+    """(kernel_x, kernel_y, border code) when the request lies inside the fused kernel's envelope -- fp32 (B,C,H,W),
+    square odd kernel of 3..11 taps, non-circular border, positive sigmas -- else None (the caller composes, and
+    gaussian_blur2d words any error).  Pure host logic."""
+    from .. import _lib
+    from .gaussian import _constant_taps, _taps
 
-    if not (isinstance(input, torch.Tensor) and input.is_cuda and input.dtype == torch.float32 and input.dim() == 4 and input.numel() > 0):
+    if not (isinstance(input, torch.Tensor) and input.dtype == torch.float32 and input.dim() == 4 and input.numel() > 0):
         return None
     ks = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
     if len(ks) != 2 or ks[0] != ks[1] or not isinstance(ks[0], int) or ks[0] % 2 == 0 or not 3 <= ks[0] <= 11:
+        return None
+    if ks[0] // 2 >= min(input.shape[-2:]):
         return None
     code = _lib.BORDERS.get(str(border_type))
     if code is None or code == _lib.CIRCULAR:
         return None
     if isinstance(sigma, tuple):
         if len(sigma) != 2 or not all(float(v) > 0 for v in sigma):
-            return None  # let gaussian_blur2d word the error
-        kx, ky = G._constant_taps(kernel_size, tuple(float(v) for v in sigma), True, input.device, input.dtype)
+            return None
+        kx, ky = _constant_taps(kernel_size, tuple(float(v) for v in sigma), True, input.device, input.dtype)
     elif isinstance(sigma, torch.Tensor) and sigma.dim() == 2 and sigma.shape[-1] == 2:
         st = sigma.to(device=input.device, dtype=input.dtype)
-        if not bool((st > 0).all()) or input.shape[0] % st.shape[0] != 0:
+        if input.shape[0] % st.shape[0] != 0 or not bool((st > 0).all()):  # the sync the reference pays too (gaussian.py:107)
             return None
-        kx, ky = G._taps(kernel_size, st, True)
+        kx, ky = _taps(kernel_size, st, True)
     else:
         return None
-    B, C, H, W = input.shape
-    if ks[0] // 2 >= min(H, W):
+    return kx.contiguous(), ky.contiguous(), code
+
+
+def _fused_unsharp(input, kernel_size, sigma, border_type):
+    """kb200_sepfilter_lerp_forward on the blur's own taps; None when the request is outside the fused envelope."""
+    from .. import _lib, _ops
+
+    if not (isinstance(input, torch.Tensor) and input.is_cuda):
         return None
+    req = _fused_request(input, kernel_size, sigma, border_type)
+    if req is None:
+        return None
+    kx, ky, code = req
+    B, C, H, W = input.shape
     x = input.contiguous()
-    kx, ky = kx.contiguous(), ky.contiguous()
     out = torch.empty_like(x)
     try:
         with torch.cuda.device(x.device), _ops._Timed("sepfilter_lerp_forward", x):

@@ -182,3 +182,21 @@ def test_install_rebinds_every_importer_of_the_reference():
     finally:
         sys.path.remove(stub)
         sys.path.remove("/root/reference")
+
+
+def test_fused_unsharp_request_host_logic():
+    """The envelope test + tap preparation in front of kb200_sepfilter_lerp_forward is pure host logic."""
+    from kornia_b200.filters.unsharp import _fused_request
+
+    x = torch.rand(2, 3, 20, 24)
+    kx, ky, code = _fused_request(x, (5, 5), (1.5, 1.5), "reflect")
+    assert kx.shape == (1, 5) and ky.shape == (1, 5) and code == K._lib.REFLECT
+    composed = torch.lerp(R.filter2d_separable(x, kx, ky, "reflect"), x, 2.0)
+    torch.testing.assert_close(composed, R.unsharp_mask(x, (5, 5), (1.5, 1.5)), rtol=0, atol=0)
+    kx, ky, code = _fused_request(x, 5, torch.tensor([[1.0, 2.0], [0.5, 0.7]]), "replicate")
+    assert kx.shape == (2, 5) and code == K._lib.REPLICATE
+    torch.testing.assert_close(kx, R.gaussian_taps(5, torch.tensor([[2.0], [0.7]])), rtol=0, atol=0)   # x taps from sigma[:, 1]
+    for bad in ((x, (3, 5), (1.0, 1.0), "reflect"), (x, (5, 5), (1.0, 1.0), "circular"), (x, (5, 5), (-1.0, 1.0), "reflect"),
+                (x.double(), (5, 5), (1.0, 1.0), "reflect"), (x, 13, (1.0, 1.0), "reflect"), (x, 4, (1.0, 1.0), "reflect"),
+                (x[0], 5, (1.0, 1.0), "reflect"), (x, 5, torch.ones(3, 2), "reflect"), (torch.rand(1, 1, 2, 9), 5, (1.0, 1.0), "reflect")):
+        assert _fused_request(*bad) is None
