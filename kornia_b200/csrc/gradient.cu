@@ -28,7 +28,7 @@ static int forward_t(const void* x, const double* taps, void* out, int planes, i
   if (rc) return rc;
   KB_CHECK_ARG(x && out, "null tensor");
   KB_CHECK_ARG(!magnitude || nout == 2, "the magnitude needs exactly two derivative outputs");
-  const dim3 block(32, 8), grid(ceil_div(W, 128), ceil_div(H, 8 * GRAD_RY), min(planes, 65535));
+  const dim3 block(32, 8), grid(ceil_div(W, 128), ceil_div(H, 8), min(planes, 65535));
   if (magnitude) {
     KB_CHECK_ARG(k == 3, "the magnitude is defined on first-order 3x3 stencils");
     spatial_gradient_fwd<T, 3, 2, true><<<grid, block, 0, st>>>(p);

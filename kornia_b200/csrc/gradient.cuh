@@ -7,9 +7,8 @@
 // produced from the same window in registers:
 //   spatial_gradient: 4 B read + 4*NOUT B written per element (reference: >= 8 + 4 + 4*NOUT)
 //   sobel magnitude : 4 B read + 4 B written per element     (reference: >= 12 + 8 + 9*4 more)
-// Each thread produces a 4-wide, 4-tall block of outputs: it walks the 4+k-1 input rows once (per row one aligned
-// 16-byte load plus 2*(k/2) halo scalars) and feeds every output row the input row overlaps; NOUT*k*k FMAs per
-// output with the taps as kernel-parameter (constant bank) operands.  A CTA covers 128 x 32 outputs.
+// Each thread produces 4 neighbouring outputs of one row: per tap row one aligned 16-byte load plus
+// 2*(k/2) halo scalars, then NOUT*k*4 FMAs with the taps as kernel-parameter (constant bank) operands.
 #pragma once
 #include "filter_generic.cuh"
 
@@ -31,35 +30,28 @@ struct GradParams {
 __device__ __forceinline__ float sqrt_rn(float v) { return __fsqrt_rn(v); }
 __device__ __forceinline__ double sqrt_rn(double v) { return __dsqrt_rn(v); }
 
-constexpr int GRAD_RY = 4;  // output rows per thread
-
 template <typename T, int K, int NOUT, bool MAG>
 __global__ void __launch_bounds__(256) spatial_gradient_fwd(const __grid_constant__ GradParams<T> p) {
   static_assert(K <= GRAD_MAX_K && NOUT <= GRAD_MAX_OUT && (!MAG || NOUT == 2), "stencil limits");
   constexpr int HALO = K / 2;
-  constexpr int RY = GRAD_RY;
-  // a thread owns a 4-wide, RY-tall block of outputs: it walks the RY+K-1 input rows once, each row window
-  // (one aligned 16-byte load + 2*HALO scalars) feeding every output row it overlaps
   const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-  const int y0 = (blockIdx.y * 8 + threadIdx.y) * RY;
-  if (x0 >= p.W || y0 >= p.H) return;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x0 >= p.W || y >= p.H) return;
   const bool inner = x0 - HALO >= 0 && x0 + 3 + HALO < p.W;  // no clamp needed along x
   const bool full = x0 + 3 < p.W;
   const size_t HW = (size_t)p.H * p.W;
 
   for (int plane = blockIdx.z; plane < p.planes; plane += gridDim.z) {
     const T* xp = p.x + (size_t)plane * HW;
-    T acc[NOUT][RY][4];
+    T acc[NOUT][4];
 #pragma unroll
     for (int o = 0; o < NOUT; ++o)
 #pragma unroll
-      for (int r = 0; r < RY; ++r)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[o][r][q] = T(0);
+      for (int q = 0; q < 4; ++q) acc[o][q] = T(0);
 
 #pragma unroll
-    for (int ir = 0; ir < RY + K - 1; ++ir) {
-      const int sy = min(max(y0 + ir - HALO, 0), p.H - 1);
+    for (int i = 0; i < K; ++i) {
+      const int sy = min(max(y + i - HALO, 0), p.H - 1);
       const T* row = xp + (size_t)sy * p.W;
       T win[4 + K - 1];
       if (inner) {
@@ -79,52 +71,40 @@ __global__ void __launch_bounds__(256) spatial_gradient_fwd(const __grid_constan
 #pragma unroll
         for (int e = 0; e < 4 + K - 1; ++e) win[e] = ldg(row + min(max(x0 - HALO + e, 0), p.W - 1));
       }
-      // input row ir is tap row i = ir - r of output row r: ascending ir means ascending (i, j) per output,
-      // the accumulation order of the gather formulation
 #pragma unroll
-      for (int r = 0; r < RY; ++r) {
-        if (ir - r >= 0 && ir - r < K) {
+      for (int j = 0; j < K; ++j)
 #pragma unroll
-          for (int j = 0; j < K; ++j)
+        for (int o = 0; o < NOUT; ++o) {
+          const T t = p.taps[(o * K + i) * K + j];
 #pragma unroll
-            for (int o = 0; o < NOUT; ++o) {
-              const T t = p.taps[(o * K + (ir - r)) * K + j];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) acc[o][r][q] = RN<T>::fma(t, win[q + j], acc[o][r][q]);
-            }
+          for (int q = 0; q < 4; ++q) acc[o][q] = RN<T>::fma(t, win[q + j], acc[o][q]);
         }
-      }
     }
 
+    if (MAG) {
+      // sqrt(gx*gx + gy*gy + eps): one rounding per reference op (sobel.py:166)
+      T* op = p.out + (size_t)plane * HW + (size_t)y * p.W + x0;
+      T m[4];
 #pragma unroll
-    for (int r = 0; r < RY; ++r) {
-      const int y = y0 + r;
-      if (y >= p.H) break;
-      if (MAG) {
-        // sqrt(gx*gx + gy*gy + eps): one rounding per reference op (sobel.py:166)
-        T* op = p.out + (size_t)plane * HW + (size_t)y * p.W + x0;
-        T m[4];
+      for (int q = 0; q < 4; ++q)
+        m[q] = sqrt_rn(RN<T>::add(RN<T>::add(RN<T>::mul(acc[0][q], acc[0][q]), RN<T>::mul(acc[1][q], acc[1][q])), p.eps));
+      if (full && p.vec && sizeof(T) == 4) {
+        __stcs(reinterpret_cast<float4*>(op), make_float4(m[0], m[1], m[2], m[3]));
+      } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          m[q] = sqrt_rn(RN<T>::add(RN<T>::add(RN<T>::mul(acc[0][r][q], acc[0][r][q]), RN<T>::mul(acc[1][r][q], acc[1][r][q])), p.eps));
+          if (x0 + q < p.W) st_stream(op + q, m[q]);
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) {
+        T* op = p.out + ((size_t)plane * NOUT + o) * HW + (size_t)y * p.W + x0;
         if (full && p.vec && sizeof(T) == 4) {
-          __stcs(reinterpret_cast<float4*>(op), make_float4(m[0], m[1], m[2], m[3]));
+          __stcs(reinterpret_cast<float4*>(op), make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]));
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (x0 + q < p.W) st_stream(op + q, m[q]);
-        }
-      } else {
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) {
-          T* op = p.out + ((size_t)plane * NOUT + o) * HW + (size_t)y * p.W + x0;
-          if (full && p.vec && sizeof(T) == 4) {
-            __stcs(reinterpret_cast<float4*>(op), make_float4(acc[o][r][0], acc[o][r][1], acc[o][r][2], acc[o][r][3]));
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (x0 + q < p.W) st_stream(op + q, acc[o][r][q]);
-          }
+            if (x0 + q < p.W) st_stream(op + q, acc[o][q]);
         }
       }
     }

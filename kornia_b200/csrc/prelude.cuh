@@ -166,8 +166,8 @@ __device__ __forceinline__ float sin_t(float v) { return sinf(v); }
 __device__ __forceinline__ double sin_t(double v) { return sin(v); }
 
 // get_rotation_matrix2d (imgwarp.py:607-622) in one launch: T(c) @ R(angle) @ S(scale) @ T(-c), the three 3x3
-// products accumulated like torch's batched GEMM, the angle converted like deg2rad (conversions.py:148: times the
-// fp32 constant pi, divided by 180).  Replaces ~35 tiny torch launches on the rotate / scale / RandomAffine path.
+// products accumulated like torch's batched GEMM, the angle converted like deg2rad on the device (conversions.py:148:
+// times the fp32 constant pi, then "divided" by 180 the way torch's CUDA scalar division does it).  Replaces ~35 tiny torch launches on the rotate / scale / RandomAffine path.
 template <typename T>
 __global__ void rotation_matrix2d_kernel(const T* __restrict__ center, const T* __restrict__ angle, const T* __restrict__ scale,
                                          T* __restrict__ out, int B, int variant) {
@@ -175,7 +175,8 @@ __global__ void rotation_matrix2d_kernel(const T* __restrict__ center, const T* 
   if (b >= B) return;
   using R = RN<T>;
   const T cx = center[2 * b], cy = center[2 * b + 1];
-  const T rad = R::div(R::mul(angle[b], (T)3.14159265358979323846f), (T)180.0);
+  // deg2rad: (angle * pi) / 180.0 -- torch's CUDA division by a host scalar multiplies by the rounded reciprocal
+  const T rad = R::mul(R::mul(angle[b], (T)3.14159265358979323846f), R::div(T(1), T(180)));
   const T c = cos_t(rad), s = sin_t(rad);
   const T to_c[9] = {T(1), T(0), cx, T(0), T(1), cy, T(0), T(0), T(1)};
   const T from_c[9] = {T(1), T(0), -cx, T(0), T(1), -cy, T(0), T(0), T(1)};
