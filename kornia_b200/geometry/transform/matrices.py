@@ -56,6 +56,7 @@ def _fused_rotation(center: torch.Tensor, angle: torch.Tensor, scale: torch.Tens
     return out
 
 
+@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def get_rotation_matrix2d(center: torch.Tensor, angle: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """(B,2,3) rotation by ``angle`` degrees (counter-clockwise on screen) and per-axis ``scale``
     about ``center`` (x, y): T(c) @ R @ S @ T(-c)."""
@@ -139,6 +140,7 @@ class _FusedPerspective(torch.autograd.Function):
         return tuple(grads.pop(0) if need else None for need in ctx.needs_input_grad)
 
 
+@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def get_perspective_transform(points_src: torch.Tensor, points_dst: torch.Tensor) -> torch.Tensor:
     """(B,3,3) homography taking the four ``points_src`` (B,4,2; x,y) onto ``points_dst``, scaled so
     that H[2,2] = 1: H = Q(dst) @ Q(src)^-1 with Q the unit-square-to-quad map (imgwarp.py:444-527).
