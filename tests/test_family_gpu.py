@@ -64,7 +64,7 @@ def test_family_filter_grads_fp64_match_oracle(name):
     got = family_grads(K.filters, op, kw, ins, outs, device=DEV, dtype=torch.float64)
     want = family_grads(R, op, kw, ins, outs, dtype=torch.float64)
     for key in want:
-        assert rel_l2(got[key].cpu(), want[key]) < 1e-11, key
+        assert rel_l2(got[key].cpu(), want[key]) < 1e-9, key
 
 
 def test_spatial_gradient_gradcheck():

@@ -119,9 +119,9 @@ def test_filter_fp64_matches_oracle(name):
     want = run_case(R, op, kw, ins, dtype=torch.float64)
     if isinstance(want, dict):
         for key in want:
-            assert rel_l2(got[key].cpu(), want[key]) < 1e-10, key
+            assert rel_l2(got[key].cpu(), want[key]) < 1e-9, key
     else:
-        torch.testing.assert_close(got.cpu(), want, rtol=1e-10, atol=1e-11)
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-9, atol=1e-10)  # host fp64 BLAS varies at the 1e-11 level from box to box
 
 
 # ------------------------------------------------------------------ gradcheck (reference: testing/base.py:158-206)

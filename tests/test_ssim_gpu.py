@@ -84,4 +84,4 @@ def test_ssim_odd_shapes_and_offsets():
     nc = torch.rand(2, 3, 40, 96, device=DEV)[:, :, :, ::2]   # non-contiguous input
     torch.testing.assert_close(K.metrics.ssim(nc, nc.flip(-1), 5), R.ssim(nc.contiguous(), nc.flip(-1).contiguous(), 5), **TOL)
     d = torch.rand(2, 2, 12, 14, device=DEV, dtype=torch.float64)  # fp64: composed path
-    torch.testing.assert_close(K.metrics.ssim(d, d.flip(-1), 5).cpu(), R.ssim(d.cpu(), d.flip(-1).cpu(), 5), rtol=1e-9, atol=1e-11)
+    torch.testing.assert_close(K.metrics.ssim(d, d.flip(-1), 5).cpu(), R.ssim(d.cpu(), d.flip(-1).cpu(), 5), rtol=1e-9, atol=1e-10)
