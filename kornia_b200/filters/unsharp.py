@@ -15,8 +15,8 @@ def unsharp_mask(input: torch.Tensor, kernel_size: tuple[int, int] | int, sigma:
     """Sharpen: ``2 * input - gaussian_blur2d(input)``, evaluated as the reference's ``lerp(blur, input, 2)`` so
     the rounding matches.  Without a gradient the blend runs in the epilogue of the blur kernel (one pass over the
     image instead of two kernels and five full-size tensor streams); with one, blur and ``torch.lerp`` compose."""
-    if not (torch.is_grad_enabled() and isinstance(input, torch.Tensor) and input.requires_grad
-            or isinstance(sigma, torch.Tensor) and torch.is_grad_enabled() and sigma.requires_grad):
+    needs_grad = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in (input, sigma))
+    if not needs_grad:
         fused = _fused_unsharp(input, kernel_size, sigma, border_type)
         if fused is not None:
             return fused
