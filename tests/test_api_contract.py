@@ -176,3 +176,31 @@ def test_c_abi_version_and_error_channel():
     assert rc == -1 and b"null src" in lib.kb200_last_error()
     rc = lib.kb200_filter2d_forward(ctypes.c_void_p(8), ctypes.c_void_p(8), ctypes.c_void_p(8), 3, 1, 4, 4, 2, 3, 3, 1, 1, 0, None)
     assert rc == -1 and b"must divide" in lib.kb200_last_error()
+
+
+def test_c_abi_validation_of_the_caller_entry_points():
+    """Entry points behind the callers of the path (spatial_gradient / sobel, ssim, unsharp, the two matrix builders):
+    bad requests are refused on the host, before any CUDA call, with the documented status."""
+    lib = _lib.load()
+    p8 = ctypes.c_void_p(8)  # non-null dummy; never dereferenced on these paths
+    taps = (ctypes.c_double * 18)(*([0.0] * 18))
+    assert lib.kb200_spatial_gradient_forward(p8, taps, p8, 6, 8, 8, 2, 4, 0, 0.0, 0, None) == -1          # 4x4 stencils do not exist
+    assert b"unsupported stencil" in lib.kb200_last_error()
+    assert lib.kb200_spatial_gradient_forward(p8, taps, p8, 6, 8, 8, 3, 3, 1, 1e-6, 0, None) == -1         # magnitude needs two outputs
+    assert lib.kb200_spatial_gradient_forward(p8, None, p8, 6, 8, 8, 2, 3, 0, 0.0, 0, None) == -1 and b"null taps" in lib.kb200_last_error()
+    assert lib.kb200_spatial_gradient_backward(p8, taps, p8, 0, 8, 8, 2, 3, 0, None) == -1                 # no planes
+    assert lib.kb200_spatial_gradient_forward(p8, taps, p8, 6, 8, 8, 2, 3, 0, 0.0, 7, None) == -1 and b"bad dtype" in lib.kb200_last_error()
+    assert lib.kb200_ssim_forward(p8, p8, p8, p8, 6, 8, 8, 5, 1e-4, 9e-4, 1e-12, 1, None) == -3            # fp64 -> the host composes
+    assert lib.kb200_ssim_forward(p8, p8, p8, p8, 6, 8, 8, 13, 1e-4, 9e-4, 1e-12, 0, None) == -3 and b"up to 11 taps" in lib.kb200_last_error()
+    assert lib.kb200_ssim_forward(p8, p8, p8, p8, 6, 8, 8, 4, 1e-4, 9e-4, 1e-12, 0, None) == -3            # even window
+    assert lib.kb200_ssim_forward(p8, None, p8, p8, 6, 8, 8, 5, 1e-4, 9e-4, 1e-12, 0, None) == -1
+    assert lib.kb200_ssim_forward(p8, p8, p8, p8, 6, 2, 8, 5, 1e-4, 9e-4, 1e-12, 0, None) == -1 and b"reflect border" in lib.kb200_last_error()
+    assert lib.kb200_sepfilter_lerp_forward(p8, p8, p8, p8, 2, 3, 8, 8, 1, 5, 1, 5, 1, 1, 2.0, 1, None) == -3  # fp64
+    assert lib.kb200_sepfilter_lerp_forward(p8, p8, p8, p8, 2, 3, 8, 8, 1, 13, 1, 13, 1, 1, 2.0, 0, None) == -3  # > 11 taps
+    assert lib.kb200_sepfilter_lerp_forward(p8, p8, p8, p8, 2, 3, 8, 8, 1, 5, 1, 5, 3, 1, 2.0, 0, None) == -3   # circular border
+    assert lib.kb200_sepfilter_lerp_forward(p8, p8, None, p8, 2, 3, 8, 8, 1, 5, 1, 5, 1, 1, 2.0, 0, None) == -1
+    assert lib.kb200_rotation_matrix2d(p8, p8, p8, p8, 0, 0, 4, None) == -1
+    assert lib.kb200_rotation_matrix2d(p8, None, p8, p8, 4, 0, 4, None) == -1
+    assert lib.kb200_perspective_from_points(p8, p8, None, 4, 0, 4, None) == -1
+    assert lib.kb200_perspective_from_points(p8, p8, p8, 4, 3, 4, None) == -1 and b"bad dtype" in lib.kb200_last_error()
+    assert isinstance(lib.kb200_last_warp_launches(), int)
