@@ -496,3 +496,140 @@ def ssim_loss(img1, img2, window_size, max_val=1.0, eps=1e-12, reduction="mean",
     """kornia/losses/ssim.py:67-82."""
     loss = torch.clamp((1.0 - ssim(img1, img2, window_size, max_val, eps, padding)) / 2, min=0, max=1)
     return loss.mean() if reduction == "mean" else loss.sum() if reduction == "sum" else loss
+
+
+# --------------------------------------------------------------------------------------
+# Pyramids, resize family, lens model (SURVEY.md 8f rows 2-4)
+# --------------------------------------------------------------------------------------
+def pyramid_taps() -> torch.Tensor:
+    """kornia/geometry/transform/pyramid.py:32-47: the 5x5 literal, which is outer([1,4,6,4,1]) / 256."""
+    b = torch.tensor([1.0, 4.0, 6.0, 4.0, 1.0])
+    return torch.outer(b, b).unsqueeze(0) / 256.0
+
+
+def pyrdown(input, border_type="reflect", align_corners=False, factor=2.0):
+    """pyramid.py:444-457: filter2d with the pyramid taps, then F.interpolate(bilinear) onto
+    (int(H / factor), int(W // factor))."""
+    hh, ww = input.shape[2], input.shape[3]
+    low = filter2d(input, pyramid_taps(), border_type)
+    return F.interpolate(low, size=(int(float(hh) / factor), int(float(ww) // factor)), mode="bilinear", align_corners=align_corners)
+
+
+def pyrup(input, border_type="reflect", align_corners=False):
+    """pyramid.py:489-502: F.interpolate(bilinear) onto (2H, 2W), then filter2d with the pyramid taps."""
+    big = F.interpolate(input, size=(2 * input.shape[2], 2 * input.shape[3]), mode="bilinear", align_corners=align_corners)
+    return filter2d(big, pyramid_taps(), border_type)
+
+
+def build_pyramid(input, max_level, border_type="reflect", align_corners=False):
+    """pyramid.py:551-560."""
+    out = [input]
+    while len(out) < max_level:
+        out.append(pyrdown(out[-1], border_type, align_corners))
+    return out
+
+
+def build_laplacian_pyramid(input, max_level, border_type="reflect", align_corners=False):
+    """pyramid.py:632-665: reflect-pad right/bottom to the next powers of two unless H or W is one already; level i is
+    gaussian[i] - pyrup(gaussian[i+1]); the coarsest gaussian level closes the list."""
+    h, w = input.shape[2], input.shape[3]
+    pow2 = lambda v: v != 0 and (v & (v - 1)) == 0  # noqa: E731
+    if not pow2(h) and not pow2(w):
+        input = F.pad(input, (0, (1 << (w - 1).bit_length()) - w, 0, (1 << (h - 1).bit_length()) - h), "reflect")
+    g = build_pyramid(input, max_level, border_type, align_corners)
+    return [a - pyrup(b, border_type, align_corners) for a, b in zip(g[:-1], g[1:])] + [g[-1]]
+
+
+def resize(input, size, interpolation="bilinear", align_corners=None, side="short", antialias=False):
+    """kornia/geometry/transform/affwarp.py:576-585,631-676: int size -> (h, w) by aspect ratio and side; leading
+    dims folded into a batch; optional Gaussian pre-blur with sigma = max((factor - 1) / 2, 0.001) and an odd window
+    of about 4 sigma (>= 3) when shrinking; F.interpolate."""
+    lead, (h, w) = input.shape[:-2], input.shape[-2:]
+    if isinstance(size, int):
+        ar = w / h
+        if side == "vert" or (side in ("short", "long") and ((side == "short") != (ar < 1.0))):
+            size = (size, int(size * ar))
+        else:
+            size = (int(size / ar), size)
+    x = input.reshape((-1,) + tuple(input.shape[-3:])) if input.dim() >= 4 else input.reshape((1,) * (4 - input.dim()) + tuple(input.shape))
+    fy, fx = h / size[0], w / size[1]
+    if antialias and max(fy, fx) > 1:
+        sig = (max((fy - 1.0) / 2.0, 0.001), max((fx - 1.0) / 2.0, 0.001))
+        win = [int(max(4.0 * s, 3)) for s in sig]
+        win = tuple(k + 1 - (k % 2) for k in win)
+        x = gaussian_blur2d(x, win, sig)
+    y = F.interpolate(x, size=tuple(size), mode=interpolation, align_corners=align_corners)
+    return y.reshape(tuple(lead) + (size[0], size[1]))
+
+
+def rescale(input, factor, interpolation="bilinear", align_corners=None, antialias=False):
+    """affwarp.py:756-763."""
+    fv, fh = (factor, factor) if isinstance(factor, float) else factor
+    return resize(input, (int(input.shape[-2] * fv), int(input.shape[-1] * fh)), interpolation, align_corners, "short", antialias)
+
+
+def resize_to_be_divisible(input, divisible_factor, interpolation="bilinear", align_corners=None, side="short", antialias=False):
+    """affwarp.py:707-715."""
+    hh = round(input.shape[-2] / divisible_factor) * divisible_factor
+    ww = round(input.shape[-1] / divisible_factor) * divisible_factor
+    return resize(input, (hh, ww), interpolation, align_corners, side, antialias)
+
+
+def tilt_projection(taux, tauy, return_inverse=False):
+    """kornia/geometry/calibration/distort.py:25-75.  The 'inverse' form is the reference's R^T @ Pz^-1 (distort.py:58-66),
+    used with row-vector points in undistort_points -- not the matrix inverse of the forward form."""
+    if not return_inverse:
+        return tilt_matrix(taux, tauy)
+    tx, ty = taux.reshape(-1), tauy.reshape(-1)
+    z, u = torch.zeros_like(tx), torch.ones_like(tx)
+    Rx = torch.stack([u, z, z, z, tx.cos(), tx.sin(), z, -tx.sin(), tx.cos()], -1).reshape(-1, 3, 3)
+    Ry = torch.stack([ty.cos(), z, -ty.sin(), z, u, z, ty.sin(), z, ty.cos()], -1).reshape(-1, 3, 3)
+    R = Ry @ Rx
+    i22 = 1 / R[..., 2, 2]
+    Pinv = torch.stack([i22, z, R[..., 0, 2] * i22, z, i22, R[..., 1, 2] * i22, z, z, u], -1).reshape(-1, 3, 3)
+    return R.transpose(-1, -2) @ Pinv
+
+
+def tilt_matrix(taux, tauy):
+    """kornia/geometry/calibration/distort.py:38-75 (forward form): Pz @ R^T with R = Ry @ Rx."""
+    tx, ty = taux.reshape(-1), tauy.reshape(-1)
+    z, u = torch.zeros_like(tx), torch.ones_like(tx)
+    Rx = torch.stack([u, z, z, z, tx.cos(), tx.sin(), z, -tx.sin(), tx.cos()], -1).reshape(-1, 3, 3)
+    Ry = torch.stack([ty.cos(), z, -ty.sin(), z, u, z, ty.sin(), z, ty.cos()], -1).reshape(-1, 3, 3)
+    R = Ry @ Rx
+    Pz = torch.stack([R[..., 2, 2], z, -R[..., 0, 2], z, R[..., 2, 2], -R[..., 1, 2], z, z, u], -1).reshape(-1, 3, 3)
+    return Pz @ R.transpose(-1, -2)
+
+
+def distort_points(points, K, dist, new_K=None):
+    """distort.py:117-189: (points - c') / f' -> rational radial factor, tangential and thin-prism terms, optional
+    tilt -> f * (.) + c."""
+    Kn = K if new_K is None else new_K
+    if dist.shape[-1] < 14:
+        dist = F.pad(dist, [0, 14 - dist.shape[-1]])
+    k1, k2, p1, p2, k3, k4, k5, k6, s1, s2, s3, s4 = (dist[..., i:i + 1] for i in range(12))
+    x = (points[..., 0] - Kn[..., 0:1, 2]) / Kn[..., 0:1, 0]
+    y = (points[..., 1] - Kn[..., 1:2, 2]) / Kn[..., 1:2, 1]
+    r2 = x * x + y * y
+    r4 = r2 * r2
+    r6 = r4 * r2
+    ratio = (1 + k1 * r2 + k2 * r4 + k3 * r6) / (1 + k4 * r2 + k5 * r4 + k6 * r6)
+    xd = x * ratio + 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + s1 * r2 + s2 * r4
+    yd = y * ratio + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + s3 * r2 + s4 * r4
+    if bool((dist[..., 12] != 0).any()) or bool((dist[..., 13] != 0).any()):
+        hom = torch.stack([xd, yd, torch.ones_like(xd)], -1) @ tilt_matrix(dist[..., 12], dist[..., 13]).transpose(-2, -1)
+        xd, yd = hom[..., 0] / hom[..., 2], hom[..., 1] / hom[..., 2]
+    return torch.stack([K[..., 0:1, 0] * xd + K[..., 0:1, 2], K[..., 1:2, 1] * yd + K[..., 1:2, 2]], -1)
+
+
+def undistort_image(image, K, dist):
+    """kornia/geometry/calibration/undistort.py:183-198: pixel grid (grid.py:65-79, unnormalised) -> distort_points
+    -> remap(align_corners=True)."""
+    C, H, W = image.shape[-3:]
+    n = image.numel() // (C * H * W)
+    xs = torch.linspace(0, W - 1, W, device=image.device, dtype=image.dtype)
+    ys = torch.linspace(0, H - 1, H, device=image.device, dtype=image.dtype)
+    grid = torch.stack([xs[None, :].expand(H, W), ys[:, None].expand(H, W)], -1).reshape(-1, 2)
+    moved = distort_points(grid, K, dist)
+    out = remap(image.reshape(n, C, H, W), moved[..., 0].reshape(n, H, W), moved[..., 1].reshape(n, H, W), align_corners=True)
+    return out.view_as(image)
