@@ -135,6 +135,17 @@ int kb200_sepfilter_lerp_forward(const void* x, const void* kernel_x, const void
                                  int W, int Bkx, int kw, int Bky, int kh, int border, int same, double weight, int dtype,
                                  void* stream);
 
+/* pyrdown (geometry/transform/pyramid.py:444-457: filter2d with the 5x5 pyramid taps, then F.interpolate(bilinear,
+ * align_corners=False) onto exactly half the size) in ONE pass: the 2x2 average that the resampling reduces to at a
+ * factor of two is the epilogue of the tiled 5x5 kernel, so the blurred full-size image never reaches HBM (4 B read +
+ * 1 B written per input element instead of 8 + 5).  x (B,C,H,W), kernel (Bk,5,5) as in kb200_filter2d_forward,
+ * out (B,C,H/2,W/2).  fp32, H even, W % 4 == 0, constant / reflect / replicate: anything else returns
+ * KB200_EUNSUPPORTED and the host composes kb200_filter2d_forward with the resampling.
+ * Status: written after the round-1 GPU budget was spent -- compiled for sm_100a, not yet run on hardware; the Python
+ * layer only calls it when KB200_FUSED_PYRDOWN=1. */
+int kb200_pyrdown_forward(const void* x, const void* kernel, void* out, int B, int C, int H, int W, int Bk, int border,
+                          int dtype, void* stream);
+
 /* get_perspective_transform (geometry/transform/imgwarp.py:444-462: two unit-square-to-quad maps, a closed-form
  * 3x3 inverse, one bmm and a scale -- ~45 tiny torch launches) in one launch, for the RandomPerspective /
  * crop_and_resize callers.  points_src, points_dst: (B,4,2) x,y corners; H_out: (B,3,3)

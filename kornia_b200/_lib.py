@@ -42,6 +42,7 @@ SIGNATURES = {
     "kb200_filter2d_backward_input": (_i, [_vp] * 3 + [_i] * 10 + [_vp]),
     "kb200_filter2d_backward_kernel_workspace_bytes": (_sz, [_i] * 8),
     "kb200_filter2d_backward_kernel": (_i, [_vp] * 4 + [_i] * 10 + [_vp]),
+    "kb200_pyrdown_forward": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
     "kb200_sepfilter_forward": (_i, [_vp] * 4 + [_i] * 11 + [_vp]),
     "kb200_rotation_matrix2d": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "kb200_perspective_from_points": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

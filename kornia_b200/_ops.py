@@ -221,6 +221,22 @@ class Filter2dFunction(torch.autograd.Function):
         return gx, gk, None, None
 
 
+def pyrdown_fused(x: torch.Tensor, kernel: torch.Tensor, border: int) -> torch.Tensor:
+    """5x5 correlation + exact 2x bilinear decimation in one kernel (forward only): (B,C,H,W) -> (B,C,H/2,W/2).
+    Raises ``_lib.Unsupported`` outside the kernel's envelope (the caller then composes filter2d + interpolate)."""
+    _require_cuda(x, "input")
+    dt = _dtype_code(x)
+    xc, kc = x.contiguous(), kernel.contiguous()
+    B, C, H, W = xc.shape
+    out = torch.empty((B, C, H // 2, W // 2), device=x.device, dtype=x.dtype)
+    if out.numel() == 0:
+        raise _lib.Unsupported("empty output")
+    with torch.cuda.device(x.device), _Timed("pyrdown_forward", x):
+        _lib.call("kb200_pyrdown_forward", _ptr(xc), _ptr(kc), _ptr(out), B, C, H, W, kc.shape[0], border, dt, _stream(x))
+    _bump()
+    return out
+
+
 class SepFilterFunction(torch.autograd.Function):
     """Row pass then column pass in one kernel (one read + one write of the image).  The backward
     composes the 1-D adjoints: g_mid = Fy^T(gout), gx = Fx^T(g_mid), with mid = Fx(x) recomputed."""

@@ -353,6 +353,20 @@ int kb200_filter2d_forward(const void* x, const void* kernel, void* out, int B, 
   return filter2d_forward_t<double>(x, kernel, out, B, C, H, W, Bk, kh, kw, border, same, st);
 }
 
+int kb200_pyrdown_forward(const void* x, const void* kernel, void* out, int B, int C, int H, int W, int Bk, int border, int dtype,
+                          void* stream) {
+  int rc = check_filter(x, kernel, B, C, H, W, Bk, 5, 5, border, 1, dtype);
+  if (rc) return rc;
+  KB_CHECK_ARG(out, "null out");
+  if (dtype != KB200_F32) {
+    set_error("the fused pyrdown kernel is fp32 only");
+    return KB200_EUNSUPPORTED;
+  }
+  rc = pyrdown_tiled_forward((const float*)x, (const float*)kernel, (float*)out, B, C, H, W, Bk, border, (cudaStream_t)stream);
+  if (rc == KB200_EUNSUPPORTED) set_error("the fused pyrdown kernel needs an even height, a width divisible by 4 and a non-circular border");
+  return rc;
+}
+
 template <typename T>
 static int filter2d_backward_input_t(const void* gout, const void* k, void* gx, int B, int C, int H, int W, int Bk, int kh,
                                      int kw, int border, int same, cudaStream_t st) {

@@ -7,6 +7,13 @@
 // patch of the box on edge tiles ('reflect' / 'replicate').  Each thread produces a 4 x 4 block of
 // outputs from a (4+K-1)-row register window (aligned LDS.128), K*K FMAs per output, taps in
 // registers for the whole strip, tap order row-major ascending = the generic kernel's (bit-identical).
+//
+// DOWN2 (pyrdown, kornia/geometry/transform/pyramid.py:444-457): the epilogue averages each 2 x 2 block of the
+// thread's 4 x 4 filtered outputs and writes the (H/2, W/2) image -- F.interpolate(bilinear, align_corners=False) at an
+// exact factor of two samples at 2 d + 0.5, i.e. both lambdas are 1/2 and ATen's
+// h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d) is 0.25 * ((a + b) + (c + d)) with one rounding per add (scaling by
+// a power of two is exact, with or without FMA contraction).  The filtered full-size image never reaches HBM:
+// 4 B read + 1 B written per input element instead of 8 + 5.
 #pragma once
 #include "sepfilter_tiled.cuh"
 
@@ -18,7 +25,7 @@ struct F2dTiledParams {
   int C, H, W, Bk, planes;
 };
 
-template <int K, int BORDER>
+template <int K, int BORDER, bool DOWN2 = false>
 __global__ void __launch_bounds__(256, 3) filter2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                 const __grid_constant__ F2dTiledParams p) {
   constexpr int HALO = (K - 1) / 2;
@@ -87,10 +94,12 @@ __global__ void __launch_bounds__(256, 3) filter2d_tiled_kernel(const __grid_con
     float kk[K * K];
 #pragma unroll
     for (int i = 0; i < K * K; ++i) kk[i] = __ldg(p.k + (size_t)(b % p.Bk) * K * K + i);
-    float* orow = p.out + (size_t)plane * p.H * p.W + (size_t)(y0 + 4 * rg) * p.W + (size_t)tx0 * TW + 4 * q;
+    // DOWN2: the output plane is (H/2, W/2) (H even, W % 4 == 0: whole 2 x 2 blocks only) and a thread owns 2 x 2 of it
+    float* orow = DOWN2 ? p.out + (size_t)plane * (p.H / 2) * (p.W / 2) + (size_t)(y0 / 2 + 2 * rg) * (p.W / 2) + (size_t)tx0 * (TW / 2) + 2 * q
+                        : p.out + (size_t)plane * p.H * p.W + (size_t)(y0 + 4 * rg) * p.W + (size_t)tx0 * TW + 4 * q;
     const bool rows_full = y0 + TH <= p.H;
 
-    for (int tx = tx0; tx < tx1; ++tx, ++n, orow += TW) {
+    for (int tx = tx0; tx < tx1; ++tx, ++n, orow += (DOWN2 ? TW / 2 : TW)) {
       const int s = n & 1;
       float* tile = tiles + s * TILE_FLOATS;
       tma::mbar_wait(&full[s], (n >> 1) & 1);
@@ -140,7 +149,18 @@ __global__ void __launch_bounds__(256, 3) filter2d_tiled_kernel(const __grid_con
       __syncthreads();  // tile[s] consumed by every thread
       if (tid == 0) issue();
 
-      if (rows_full && (tx + 1) * TW <= p.W) {
+      if (DOWN2) {
+        if (tx * TW + 4 * q < p.W) {
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            if (y0 + 4 * rg + 2 * o < p.H) {
+              const float lo = 0.25f * __fadd_rn(__fadd_rn(acc[2 * o][0], acc[2 * o][1]), __fadd_rn(acc[2 * o + 1][0], acc[2 * o + 1][1]));
+              const float hi = 0.25f * __fadd_rn(__fadd_rn(acc[2 * o][2], acc[2 * o][3]), __fadd_rn(acc[2 * o + 1][2], acc[2 * o + 1][3]));
+              __stcs(reinterpret_cast<float2*>(orow + (size_t)o * (p.W / 2)), make_float2(lo, hi));
+            }
+          }
+        }
+      } else if (rows_full && (tx + 1) * TW <= p.W) {
         float* op = orow;
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
@@ -159,5 +179,8 @@ __global__ void __launch_bounds__(256, 3) filter2d_tiled_kernel(const __grid_con
 
 int filter2d_tiled_forward(const float* x, const float* k, float* out, int B, int C, int H, int W, int Bk, int kh, int kw, int border,
                            int same, cudaStream_t st);
+// 5 x 5 filter + 2 x 2 average in one pass: out (B,C,H/2,W/2).  KB200_EUNSUPPORTED unless H is even, W % 4 == 0 and the
+// pointers are 16 / 8-byte aligned.
+int pyrdown_tiled_forward(const float* x, const float* k, float* out, int B, int C, int H, int W, int Bk, int border, cudaStream_t st);
 
 }  // namespace kb200

@@ -9,10 +9,13 @@ traffic next to the blur's 8, left to ATen.  ``ScalePyramid`` (the SIFT octave b
 detection caller and stays out of scope."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ... import _lib, _ops
 from ...core.check import check, check_shape
 from ...filters.filter import filter2d
 
@@ -28,11 +31,35 @@ def _binomial5x5() -> torch.Tensor:
     return (row[:, None] * row[None, :])[None] / 256.0
 
 
+def _fused_request(input: torch.Tensor, border_type: str, align_corners: bool, factor: float):
+    """(taps, border code) when the one-pass kernel (kb200_pyrdown_forward: the 2x2 average that the bilinear
+    resampling reduces to at an exact factor of two runs in the blur's epilogue) may serve the call, else None.
+    Off unless KB200_FUSED_PYRDOWN=1: the kernel was written after the round's GPU budget was spent and has not run
+    on hardware yet."""
+    if os.environ.get("KB200_FUSED_PYRDOWN") != "1":
+        return None
+    if not (input.is_cuda and input.dtype == torch.float32) or (torch.is_grad_enabled() and input.requires_grad):
+        return None
+    height, width = input.shape[-2:]
+    if factor != 2.0 or align_corners or height % 2 or width % 4 or height < 4:
+        return None
+    code = _lib.BORDERS.get(str(border_type).lower())
+    if code is None or code == _lib.CIRCULAR:
+        return None
+    return _binomial5x5().to(device=input.device, dtype=input.dtype), code
+
+
 @torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def pyrdown(input: torch.Tensor, border_type: str = "reflect", align_corners: bool = False, factor: float = 2.0) -> torch.Tensor:
     """Blur with the 5x5 binomial kernel, then resample bilinearly onto (int(H / factor), int(W // factor))."""
     check_shape(input, ["B", "C", "H", "W"])
     height, width = input.shape[-2:]
+    fused = _fused_request(input, border_type, align_corners, factor)
+    if fused is not None:
+        try:
+            return _ops.pyrdown_fused(input, *fused)
+        except _lib.Unsupported:
+            pass
     blurred = filter2d(input, _binomial5x5(), border_type)
     size = (int(float(height) / factor), int(float(width) // factor))  # the reference's mixed / and // (pyramid.py:452)
     return F.interpolate(blurred, size=size, mode="bilinear", align_corners=align_corners)
