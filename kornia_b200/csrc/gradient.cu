@@ -1,5 +1,6 @@
 // kornia_b200 -- host side of the image-derivative kernels (gradient.cuh).
 #include "gradient.cuh"
+#include "gradient_tiled.cuh"
 
 namespace kb200 {
 
@@ -68,6 +69,10 @@ static int backward_t(const void* gout, const double* taps, void* gx, int planes
 
 int spatial_gradient_forward(const void* x, const double* taps, void* out, int planes, int H, int W, int nout, int k,
                              int magnitude, double eps, int dtype, cudaStream_t st) {
+  if (dtype == KB200_F32) {  // TMA tile loader (opt-in, gradient_tiled.cuh); anything it declines runs the kernel below
+    const int rc = spatial_gradient_tiled_forward((const float*)x, taps, (float*)out, planes, H, W, nout, k, magnitude, eps, st);
+    if (rc != KB200_EUNSUPPORTED) return rc;
+  }
   return dtype == KB200_F32 ? forward_t<float>(x, taps, out, planes, H, W, nout, k, magnitude, eps, st)
                             : forward_t<double>(x, taps, out, planes, H, W, nout, k, magnitude, eps, st);
 }

@@ -56,3 +56,32 @@ def test_fused_pyrdown_golden_and_fallbacks(monkeypatch):
     xg = torch.rand(1, 1, 16, 16, device=DEV, requires_grad=True)
     KT.pyrdown(xg).sum().backward()
     assert xg.grad is not None and xg.grad.shape == xg.shape
+
+
+# ------------------------------------------------------------------------------------------ tiled derivatives
+@pytest.mark.parametrize("shape", [(2, 3, 64, 128), (1, 2, 70, 132), (3, 1, 33, 260), (1, 1, 3, 4), (1, 3, 1080, 1920)])
+@pytest.mark.parametrize("mode,order", [("sobel", 1), ("diff", 1), ("sobel", 2), ("diff", 2)])
+@pytest.mark.parametrize("normalized", [True, False])
+def test_tiled_spatial_gradient_bit_identical(monkeypatch, shape, mode, order, normalized):
+    """grad_tiled_kernel (KB200_TILED_GRADIENT=1) == spatial_gradient_fwd, bit for bit (same taps, same FMA order)."""
+    x = torch.rand(*shape, device=DEV)
+    monkeypatch.delenv("KB200_TILED_GRADIENT", raising=False)
+    want = K.filters.spatial_gradient(x, mode, order, normalized)
+    monkeypatch.setenv("KB200_TILED_GRADIENT", "1")
+    got = K.filters.spatial_gradient(x, mode, order, normalized)
+    assert got.shape == want.shape and torch.equal(got, want), float((got - want).abs().max())
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 128), (1, 2, 70, 132), (1, 3, 1080, 1920)])
+def test_tiled_sobel_bit_identical_and_golden(monkeypatch, shape):
+    x = torch.rand(*shape, device=DEV)
+    monkeypatch.delenv("KB200_TILED_GRADIENT", raising=False)
+    want = K.filters.sobel(x)
+    monkeypatch.setenv("KB200_TILED_GRADIENT", "1")
+    got = K.filters.sobel(x)
+    assert torch.equal(got, want), float((got - want).abs().max())
+    FAM = golden("family")
+    for name in FAM.names("sobel") + FAM.names("spatial_gradient"):
+        op, kw, ins, outs = FAM.case(name)
+        res = getattr(K.filters, op)(ins["input"].to(DEV), **kw)
+        torch.testing.assert_close(res.cpu(), outs["out"], rtol=1e-4, atol=1e-5)

@@ -1,0 +1,46 @@
+#!/bin/bash
+# First gpurun call of round 2 (one box, one GPU; budget ~25 min of box time):
+#
+#   /usr/local/graft/bin/gpurun --timeout 1700 -- 'bash tools/r2_first_call.sh'
+#
+# Round 1 ended with the GPU budget spent before (a) the wider-caller tests, (b) the kernels of DESIGN.md section 9
+# and (c) the ncu launch list of the final build could run on hardware.  This script collects all of it in one call
+# and leaves everything under gpurun_out/r2_first/ (copy what is to be judged into profiles/).
+# Every step is bounded by its own timeout and failures do not stop the following steps.
+set -u
+OUT=gpurun_out/r2_first
+mkdir -p "$OUT"
+export PYTHONUNBUFFERED=1
+step() { echo "=== $1" | tee -a "$OUT/steps.log"; }
+
+step "1 gpu tests of the default build"
+timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider > "$OUT/pytest_gpu.log" 2>&1; echo "rc=$?" >> "$OUT/pytest_gpu.log"
+tail -3 "$OUT/pytest_gpu.log" | tee -a "$OUT/steps.log"
+
+step "2 unverified kernels (section 9): parity against the verified paths"
+KB200_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_unverified_gpu.py -m gpu -q -p no:cacheprovider > "$OUT/pytest_unverified.log" 2>&1
+echo "rc=$?" >> "$OUT/pytest_unverified.log"
+tail -15 "$OUT/pytest_unverified.log" | tee -a "$OUT/steps.log"
+
+step "3 bench lines (headline, blur, fwd+bwd) and the CPU arm"
+for wl in warp blur warp_bwd; do
+  timeout 400 python bench.py --workload $wl > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"; echo "$wl rc=$?" | tee -a "$OUT/steps.log"
+done
+timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"
+
+step "4 timings of the unverified variants against the defaults"
+timeout 400 python tools/bench_unverified.py > "$OUT/bench_unverified.txt" 2>&1; echo "rc=$?" | tee -a "$OUT/steps.log"
+timeout 300 python tools/bench_family.py > "$OUT/family_B64.txt" 2>&1
+
+step "5 ncu launch list of bench.py on this build (shares, not absolutes)"
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_bench_steps3.csv" \
+  python bench.py --steps 3 --warmup 1 --no-cpu-baseline > "$OUT/ncu_launches.log" 2>&1
+
+step "6 ncu --set full of the three BASELINE kernels (small batches: ~40 replays per launch)"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:warp_bwd_tma -s 1 -c 1 -o "$OUT/prof_bwd" \
+  python bench.py --workload warp_bwd --batch 32 --steps 1 --warmup 1 --no-cpu-baseline > "$OUT/ncu_bwd.log" 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:sepfilter_tiled -s 1 -c 1 -o "$OUT/prof_blur" \
+  python bench.py --workload blur --batch 16 --steps 1 --warmup 1 --no-cpu-baseline > "$OUT/ncu_blur.log" 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:warp_fwd_tma -s 2 -c 1 -o "$OUT/prof_fwd" \
+  python bench.py --batch 64 --steps 1 --warmup 1 --no-cpu-baseline > "$OUT/ncu_fwd.log" 2>&1
+ls -la "$OUT" | tee -a "$OUT/steps.log"
