@@ -453,6 +453,9 @@ int kb200_sepfilter_forward(const void* x, const void* kernel_x, const void* ker
   KB_CHECK_ARG((long long)B * C <= MAX_Z, "B*C = %lld planes exceed the %d-plane launch limit", (long long)B * C, MAX_Z);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == KB200_F32) {
+    rc = sepfilter_vwalk_forward((const float*)x, (const float*)kernel_x, (const float*)kernel_y, (float*)out, B, C, H, W, Bkx,
+                                 kw, Bky, kh, border, same, st);  // opt-in (KB200_SEP_VWALK=1), declines otherwise
+    if (rc != KB200_EUNSUPPORTED) return rc;
     rc = sepfilter_tiled_forward((const float*)x, (const float*)kernel_x, (const float*)kernel_y, (float*)out, B, C, H, W, Bkx,
                                  kw, Bky, kh, border, same, st);
     if (rc != KB200_EUNSUPPORTED) return rc;

@@ -85,3 +85,41 @@ def test_tiled_sobel_bit_identical_and_golden(monkeypatch, shape):
         op, kw, ins, outs = FAM.case(name)
         res = getattr(K.filters, op)(ins["input"].to(DEV), **kw)
         torch.testing.assert_close(res.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ band-walking separable filter
+@pytest.mark.parametrize("border", ["reflect", "replicate", "constant"])
+@pytest.mark.parametrize("ksize", [3, 5, 11, 17])
+@pytest.mark.parametrize("shape", [(2, 3, 70, 132), (1, 1, 32, 128), (3, 2, 33, 4), (1, 2, 97, 260), (1, 1, 6, 8), (2, 3, 1080, 1920)])
+def test_band_walk_separable_filter_bit_identical(monkeypatch, border, ksize, shape):
+    """sepfilter_vwalk_kernel (KB200_SEP_VWALK=1) == sepfilter_tiled_kernel, bit for bit: same taps, same FMA order, the
+    vertical fold applied to row-filtered rows instead of input rows.  Per-sample taps exercise the b % Bk indexing."""
+    if border != "constant" and min(shape[-2:]) <= ksize // 2:
+        pytest.skip("fold distance exceeds the image")
+    g = torch.Generator().manual_seed(ksize)
+    x = torch.rand(*shape, device=DEV)
+    kx = torch.rand(shape[0], ksize, generator=g).to(DEV)
+    ky = torch.rand(1, ksize, generator=g).to(DEV)
+    monkeypatch.delenv("KB200_SEP_VWALK", raising=False)
+    want = K.filter2d_separable(x, kx, ky, border)
+    monkeypatch.setenv("KB200_SEP_VWALK", "1")
+    got = K.filter2d_separable(x, kx, ky, border)
+    assert torch.equal(got, want), float((got - want).abs().max())
+
+
+def test_band_walk_many_segments_and_blur_golden(monkeypatch):
+    """More bands than CTAs (leftover bands are cut into runs: segments that start in the middle of a band), and the
+    gaussian_blur2d goldens of the reference through the new kernel."""
+    monkeypatch.setenv("KB200_SEP_VWALK", "1")
+    x = torch.rand(37, 3, 200, 520, device=DEV)   # 111 planes x 5 bands = 555 bands > 444 CTAs
+    got = K.gaussian_blur2d(x, (11, 11), (2.0, 2.0))
+    monkeypatch.delenv("KB200_SEP_VWALK")
+    assert torch.equal(got, K.gaussian_blur2d(x, (11, 11), (2.0, 2.0)))
+    monkeypatch.setenv("KB200_SEP_VWALK", "1")
+    FIL = golden("filter")
+    for name in FIL.names("gaussian_blur2d"):
+        op, kw, ins, outs = FIL.case(name)
+        sigma = ins["sigma"].to(DEV) if "sigma" in ins else tuple(kw["sigma"])
+        res = K.gaussian_blur2d(ins["input"].to(DEV), tuple(kw["kernel_size"]) if isinstance(kw["kernel_size"], list) else kw["kernel_size"],
+                                sigma, kw["border_type"], kw["separable"])
+        torch.testing.assert_close(res.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
