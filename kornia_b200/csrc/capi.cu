@@ -489,7 +489,10 @@ int kb200_ssim_forward(const void* img1, const void* img2, const void* taps, voi
     set_error("the fused SSIM kernel is fp32 only");
     return KB200_EUNSUPPORTED;
   }
-  int rc = ssim_tiled_forward((const float*)img1, (const float*)img2, (const float*)taps, (float*)out, planes, H, W, K, (float)C1,
+  int rc = ssim_vwalk_forward((const float*)img1, (const float*)img2, (const float*)taps, (float*)out, planes, H, W, K, (float)C1,
+                              (float)C2, (float)eps, (cudaStream_t)stream);  // opt-in (KB200_SSIM_VWALK=1), declines otherwise
+  if (rc != KB200_EUNSUPPORTED) return rc;
+  rc = ssim_tiled_forward((const float*)img1, (const float*)img2, (const float*)taps, (float*)out, planes, H, W, K, (float)C1,
                               (float)C2, (float)eps, (cudaStream_t)stream);
   if (rc == KB200_EUNSUPPORTED) set_error("the fused SSIM kernel handles odd windows up to %d taps, got %d", SSIM_MAX_K, K);
   return rc;

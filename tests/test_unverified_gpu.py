@@ -123,3 +123,34 @@ def test_band_walk_many_segments_and_blur_golden(monkeypatch):
         res = K.gaussian_blur2d(ins["input"].to(DEV), tuple(kw["kernel_size"]) if isinstance(kw["kernel_size"], list) else kw["kernel_size"],
                                 sigma, kw["border_type"], kw["separable"])
         torch.testing.assert_close(res.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ band-walking SSIM
+@pytest.mark.parametrize("window", [3, 5, 7, 9, 11])
+@pytest.mark.parametrize("shape", [(2, 3, 70, 132), (1, 1, 32, 64), (3, 2, 33, 8), (1, 2, 97, 260), (1, 1, 6, 8), (1, 3, 1080, 1920)])
+def test_band_walk_ssim_bit_identical(monkeypatch, window, shape):
+    """ssim_vwalk_kernel (KB200_SSIM_VWALK=1) == ssim_tiled_kernel, bit for bit."""
+    if min(shape[-2:]) <= window // 2:
+        pytest.skip("reflect distance exceeds the image")
+    a = torch.rand(*shape, device=DEV)
+    b = (a + 0.1 * torch.randn(*shape, device=DEV)).clamp(0, 1)
+    monkeypatch.delenv("KB200_SSIM_VWALK", raising=False)
+    want = K.metrics.ssim(a, b, window)
+    monkeypatch.setenv("KB200_SSIM_VWALK", "1")
+    got = K.metrics.ssim(a, b, window)
+    assert torch.equal(got, want), float((got - want).abs().max())
+
+
+def test_band_walk_ssim_many_segments_and_golden(monkeypatch):
+    monkeypatch.setenv("KB200_SSIM_VWALK", "1")
+    a = torch.rand(40, 3, 200, 260, device=DEV)   # 120 planes x 5 bands = 600 bands > 296 CTAs: segments start inside bands
+    b = a.flip(-1).contiguous()
+    got = K.metrics.ssim(a, b, 11)
+    monkeypatch.delenv("KB200_SSIM_VWALK")
+    assert torch.equal(got, K.metrics.ssim(a, b, 11))
+    monkeypatch.setenv("KB200_SSIM_VWALK", "1")
+    SS = golden("ssim")
+    for name in SS.names("ssim"):
+        op, kw, ins, outs = SS.case(name)
+        res = K.metrics.ssim(ins["img1"].to(DEV), ins["img2"].to(DEV), **kw)
+        torch.testing.assert_close(res.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
