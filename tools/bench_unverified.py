@@ -1,0 +1,74 @@
+"""Timing of the opt-in kernels of DESIGN.md section 9 against the defaults they would replace, on one GPU
+(B x 3 x 1080 x 1920 fp32, CUDA events, 3 warm-ups, inputs larger than L2).  Each pair is first compared bit for
+bit; a variant that differs is reported as MISMATCH and its time is not a result.
+
+    python tools/bench_unverified.py            # B = 64;  BENCH_B=256 for the BASELINE batch of cfg3
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import kornia_b200 as K  # noqa: E402
+
+dev = "cuda"
+B = int(os.environ.get("BENCH_B", "64"))
+H, W = 1080, 1920
+peak = 6568.0
+try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+x = torch.rand(B, 3, H, W, device=dev)
+y = (x + 0.05 * torch.randn_like(x)).clamp_(0, 1)
+elems = B * 3 * H * W
+
+
+def timed(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / n
+
+
+def pair(name, switch, fn, bytes_per_elem):
+    os.environ.pop(switch, None)
+    ref = fn()
+    t0 = timed(fn)
+    os.environ[switch] = "1"
+    try:
+        got = fn()
+        same = torch.equal(got, ref)
+        t1 = timed(fn)
+    except Exception as exc:  # keep going: one broken variant must not hide the others
+        print(f"{name:34s} default {t0:7.3f} ms | {switch}=1 FAILED: {exc}")
+        os.environ.pop(switch, None)
+        return
+    os.environ.pop(switch, None)
+    gb = elems * bytes_per_elem / 1e9
+    print(f"{name:34s} default {t0:7.3f} ms ({gb / t0 / peak * 1e3 * 100:5.1f} % HBM) | {switch}=1 {t1:7.3f} ms "
+          f"({gb / t1 / peak * 1e3 * 100:5.1f} % HBM) | x{t0 / t1:4.2f} | {'bit-identical' if same else 'MISMATCH'}")
+    del ref, got
+
+
+with torch.no_grad():
+    print(f"B={B} x 3 x {H} x {W} fp32, measured HBM peak {peak:.0f} GB/s; bytes = algorithmic bytes of the fused op")
+    pair("gaussian_blur2d k=11 (cfg3)", "KB200_SEP_VWALK", lambda: K.gaussian_blur2d(x, (11, 11), (2.0, 2.0)), 8)
+    pair("gaussian_blur2d k=5", "KB200_SEP_VWALK", lambda: K.gaussian_blur2d(x, (5, 5), (1.0, 1.0)), 8)
+    pair("gaussian_blur2d k=17", "KB200_SEP_VWALK", lambda: K.gaussian_blur2d(x, (17, 17), (3.0, 3.0)), 8)
+    pair("ssim window 11", "KB200_SSIM_VWALK", lambda: K.metrics.ssim(x, y, 11), 12)
+    pair("ssim window 5", "KB200_SSIM_VWALK", lambda: K.metrics.ssim(x, y, 5), 12)
+    pair("spatial_gradient sobel order 1", "KB200_TILED_GRADIENT", lambda: K.filters.spatial_gradient(x, "sobel", 1), 12)
+    pair("spatial_gradient sobel order 2", "KB200_TILED_GRADIENT", lambda: K.filters.spatial_gradient(x, "sobel", 2), 16)
+    pair("spatial_gradient diff order 2", "KB200_TILED_GRADIENT", lambda: K.filters.spatial_gradient(x, "diff", 2), 16)
+    pair("sobel magnitude", "KB200_TILED_GRADIENT", lambda: K.filters.sobel(x), 8)
+    pair("pyrdown", "KB200_FUSED_PYRDOWN", lambda: K.geometry.transform.pyrdown(x), 5)
