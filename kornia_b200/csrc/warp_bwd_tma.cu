@@ -76,6 +76,15 @@ int warp_tma_backward(const float* gout, const float* src, const float* m, const
     p.record_batch = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + rows * TMA_CONSUMER_WARPS * 9 * sizeof(float));
   }
   int rc = KB200_EUNSUPPORTED;
+  const char* v2 = getenv("KB200_BWD_V2");  // opt-in: warp-independent pipelines (warp_bwd_tma2.cuh), not yet run on hardware
+  if (v2 && v2[0] == '1') {
+    CUtensorMap msrcwin;
+    const cuuint32_t box[3] = {72, BWD_SH, (cuuint32_t)C};
+    if (encode(&msrcwin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return KB200_EUNSUPPORTED;
+    rc = launch_warp_bwd_tma2(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, st);
+  } else {
 #define KB_BWD_CASE(NC_, PAD_, PROJ_, ALIGN_)                                                                                   \
   if (C == NC_ && pad == PAD_ && (projective != 0) == PROJ_ && (align != 0) == ALIGN_) {                                       \
     if (gsrc && gm) rc = launch_warp_bwd_tma<NC_, PAD_, PROJ_, ALIGN_, true, true>(msrc, mgsrc, mgout, p, st);                         \
@@ -90,6 +99,7 @@ int warp_tma_backward(const float* gout, const float* src, const float* m, const
   KB_BWD_CASES(1, KB200_BORDER)
 #undef KB_BWD_CASES
 #undef KB_BWD_CASE
+  }
   if (rc != KB200_OK || !gm) return rc;
   warp_gm_reduce_records<<<dim3(9, Bm), 256, 0, st>>>(p.records, p.record_batch, gm, (int)rows, Bm);
   cudaError_t e = cudaGetLastError();

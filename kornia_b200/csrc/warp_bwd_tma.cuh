@@ -471,6 +471,11 @@ inline size_t bwd_tma_workspace_bytes(int B, int h) {
   return rows * (TMA_CONSUMER_WARPS * 9 * sizeof(float)) + rows * sizeof(int) + 256;
 }
 
+// Warp-independent variant (warp_bwd_tma2.cuh), opt-in with KB200_BWD_V2=1.  msrcwin: tensor map of `src` with the
+// per-warp window box (72, BWD_SH, C).
+int launch_warp_bwd_tma2(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const CUtensorMap& mgout, const TmaBwdParams& p, int C, int pad,
+                         int projective, int align, bool need_src, bool need_m, cudaStream_t st);
+
 int warp_tma_backward(const float* gout, const float* src, const float* m, const float* bx, const float* by, float* gsrc, float* gm,
                       void* workspace, int B, int C, int H, int W, int h, int w, int Bm, int projective, int interp, int pad, int align,
                       cudaStream_t st);

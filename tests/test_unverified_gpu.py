@@ -154,3 +154,82 @@ def test_band_walk_ssim_many_segments_and_golden(monkeypatch):
         op, kw, ins, outs = SS.case(name)
         res = K.metrics.ssim(ins["img1"].to(DEV), ins["img2"].to(DEV), **kw)
         torch.testing.assert_close(res.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ warp-independent backward
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+@pytest.mark.parametrize("ac", [True, False])
+@pytest.mark.parametrize("C", [3, 1])
+def test_backward_v2_matches_v1_and_generic(monkeypatch, pad, ac, C):
+    """warp_bwd_tma2 (KB200_BWD_V2=1) against warp_bwd_tma and the generic atomics kernel: same per-pixel arithmetic; d/dsrc
+    differs only by the order of the reduce-adds, d/dM by which pixels take the exact path (different windows)."""
+    from test_parity_gpu import _bench_homographies, _generic, _wild_matrices
+    from helpers import rel_l2
+
+    H, W = 120, 256
+    M = torch.cat([_wild_matrices(H, W), _bench_homographies(6, H, W, 9, sigma=3.0)]).to(DEV)
+    B = M.shape[0]
+    g = torch.Generator().manual_seed(C)
+    src = torch.rand(B, C, H, W, generator=g).to(DEV)
+    for dsize in ((H, W), (96, 200), (33, 66)):
+        cot = (torch.rand(B, C, *dsize, generator=g) - 0.5).to(DEV)
+
+        def grads(kind, want=(True, True)):
+            s = src.clone().requires_grad_(want[0])
+            if kind == "persp":
+                mm = M.clone().requires_grad_(want[1])
+                out = K.warp_perspective(s, mm, dsize, padding_mode=pad, align_corners=ac)
+            else:
+                mm = M[:, :2].clone().requires_grad_(want[1])
+                out = K.warp_affine(s, mm, dsize, padding_mode=pad, align_corners=ac)
+            return torch.autograd.grad(out, [t for t, w in zip((s, mm), want) if w], grad_outputs=cot)
+
+        for kind in ("persp", "affine"):
+            monkeypatch.delenv("KB200_BWD_V2", raising=False)
+            gs1, gm1 = grads(kind)
+            gs0, gm0 = _generic(lambda: grads(kind), check_variant=False)
+            monkeypatch.setenv("KB200_BWD_V2", "1")
+            gs2, gm2 = grads(kind)
+            (gs_only,) = grads(kind, (True, False))
+            (gm_only,) = grads(kind, (False, True))
+            monkeypatch.delenv("KB200_BWD_V2")
+            for ref in (gs1, gs0):
+                assert rel_l2(gs2, ref) < 2e-6, (kind, dsize, rel_l2(gs2, ref))
+                torch.testing.assert_close(gs2, ref, rtol=1e-4, atol=2e-5)
+            assert rel_l2(gs_only, gs2) < 2e-6
+            for b in range(B):
+                if not torch.isfinite(gm0[b]).all():
+                    continue
+                assert rel_l2(gm2[b], gm1[b]) < 1e-4 and rel_l2(gm2[b], gm0[b]) < 1e-4, (kind, dsize, b)
+                assert rel_l2(gm_only[b], gm2[b]) < 1e-5
+
+
+def test_backward_v2_720p_and_goldens(monkeypatch):
+    """cfg4's shape at reduced batch against the reference's autograd on CPU, and every golden gradient case."""
+    from helpers import rel_l2, run_case
+    from oracle import kornia_restated as R
+    from test_parity_gpu import _bench_homographies
+
+    monkeypatch.setenv("KB200_BWD_V2", "1")
+    H, W, B = 720, 1280, 2
+    M = _bench_homographies(B, H, W, 7).to(DEV)
+    yy, xx = torch.linspace(0, 1, H)[:, None], torch.linspace(0, 1, W)[None, :]
+    smooth = torch.stack([torch.stack([0.5 + 0.25 * torch.sin(6.2831853 * ((c + 1) * xx + (b + 2) * yy)) +
+                                       0.2 * torch.cos(6.2831853 * (5 * xx - 3 * yy + 0.1 * c)) for c in range(3)]) for b in range(B)])
+    target = smooth.flip(-1) * 0.5 + 0.25
+
+    def run(mod, s, m, t):
+        s, m = s.clone().requires_grad_(True), m.clone().requires_grad_(True)
+        return torch.autograd.grad(((mod.warp_perspective(s, m, (H, W)) - t) ** 2).mean(), [s, m])
+
+    gs, gm = run(K, smooth.to(DEV), M, target.to(DEV))
+    gs_ref, gm_ref = run(R, smooth, M.cpu(), target)
+    assert rel_l2(gs.cpu(), gs_ref) < 1e-4 and rel_l2(gm.cpu(), gm_ref) < 1e-3, (rel_l2(gs.cpu(), gs_ref), rel_l2(gm.cpu(), gm_ref))
+    WARP = golden("warp")
+    for op in ("warp_perspective_grad", "warp_affine_grad"):
+        for name in WARP.names(op):
+            _, kw, ins, outs = WARP.case(name)
+            got = run_case(K, op, kw, ins, device=DEV)
+            for key, want in outs.items():
+                if key != "cot":
+                    assert rel_l2(got[key].cpu(), want) < 1e-4, (name, key)
