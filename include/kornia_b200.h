@@ -104,6 +104,16 @@ int kb200_remap_backward(const void* gout, const void* src, const void* map_x, c
                          void* gmap_x, void* gmap_y, int B, int C, int H, int W, int h, int w, int Bmap,
                          int normalized, int interp, int pad, int align_corners, int dtype, void* stream);
 
+/* undistort_image (geometry/calibration/undistort.py:183-198: create_meshgrid + distort_points -- ~45 elementwise
+ * passes over (B,H*W) coordinates, calibration/distort.py:137-189 -- + remap(align_corners=True)) in ONE kernel: every
+ * output pixel evaluates the lens model in registers (one IEEE rounding per reference op) and samples; the (B,H,W)
+ * maps never exist.  lens (B,16) = fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, k5, k6, s1, s2, s3, s4 (the tilt terms of
+ * the 14-coefficient model must be zero); src and out (B,C,H,W).  fp32, C in {1,3}, W % 4 == 0: anything else returns
+ * KB200_EUNSUPPORTED and the host builds the maps and calls kb200_remap_forward.  Forward only.
+ * Status: written after the round-1 GPU budget was spent -- compiled for sm_100a, not yet run on hardware; the Python
+ * layer only calls it when KB200_FUSED_UNDISTORT=1. */
+int kb200_undistort_forward(const void* src, const void* lens, void* out, int B, int C, int H, int W, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * filter2d core (filters/filter.py:136-150: F.pad + view + depthwise F.conv2d + view).
  *   x      (B,C,H,W)

@@ -221,6 +221,22 @@ class Filter2dFunction(torch.autograd.Function):
         return gx, gk, None, None
 
 
+def undistort_fused(image: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+    """Lens model + bilinear resampling in one kernel (forward only): image (B,C,H,W), lens (B,16).  Raises
+    ``_lib.Unsupported`` outside the kernel's envelope (the caller then builds the maps and calls remap)."""
+    _require_cuda(image, "image")
+    dt = _dtype_code(image)
+    img, ln = image.contiguous(), lens.to(device=image.device, dtype=image.dtype).contiguous()
+    B, C, H, W = img.shape
+    out = torch.empty_like(img)
+    if out.numel() == 0:
+        raise _lib.Unsupported("empty image")
+    with torch.cuda.device(image.device), _Timed("undistort_forward", image):
+        _lib.call("kb200_undistort_forward", _ptr(img), _ptr(ln), _ptr(out), B, C, H, W, dt, _stream(image))
+    _bump()
+    return out
+
+
 def pyrdown_fused(x: torch.Tensor, kernel: torch.Tensor, border: int) -> torch.Tensor:
     """5x5 correlation + exact 2x bilinear decimation in one kernel (forward only): (B,C,H,W) -> (B,C,H/2,W/2).
     Raises ``_lib.Unsupported`` outside the kernel's envelope (the caller then composes filter2d + interpolate)."""

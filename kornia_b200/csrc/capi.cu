@@ -258,6 +258,16 @@ int kb200_remap_forward(const void* src, const void* map_x, const void* map_y, v
   return remap_forward_t<double>(src, map_x, map_y, out, B, C, H, W, h, w, Bmap, normalized, interp, pad, align_corners, st);
 }
 
+int kb200_undistort_forward(const void* src, const void* lens, void* out, int B, int C, int H, int W, int dtype, void* stream) {
+  KB_CHECK_ARG(src && lens && out, "null pointer argument");
+  KB_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "non-positive shape");
+  KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
+  int rc = KB200_EUNSUPPORTED;
+  if (dtype == KB200_F32) rc = undistort_tiled_forward((const float*)src, (const float*)lens, (float*)out, B, C, H, W, (cudaStream_t)stream);
+  if (rc == KB200_EUNSUPPORTED) set_error("the fused undistort kernel covers fp32 images of 1 or 3 channels with a width divisible by 4");
+  return rc;
+}
+
 template <typename T>
 static int remap_backward_t(const void* gout, const void* src, const void* mx, const void* my, void* gsrc, void* gmx, void* gmy,
                             int B, int C, int H, int W, int h, int w, int Bmap, int normalized, int interp, int pad, int align,

@@ -13,6 +13,12 @@
 // Smooth maps (undistortion, flow fields, elastic grids of moderate amplitude) fit the box; a tile whose
 // coordinates spread further simply runs on the exact path.  Algorithmic bytes: 8 (maps) + 12 + 12 per
 // RGB pixel.
+//
+// LENS (undistort_image, kornia/geometry/calibration/undistort.py:183-198): the map entry of a pixel is not read but
+// evaluated in registers from the 16 lens numbers of its sample -- distort_points (calibration/distort.py:137-189) op
+// for op, one IEEE rounding per torch op, applied to the exact integer pixel grid create_meshgrid produces -- so the
+// (B,H,W) maps and the ~45 elementwise passes that build them never exist: 24 B per RGB pixel instead of 32 + ~400.
+// Tilt coefficients (a 3x3 matmul in the reference) are not covered.  Opt-in: KB200_FUSED_UNDISTORT=1 on the host.
 #pragma once
 #include "warp_tma.cuh"
 
@@ -24,10 +30,34 @@ struct RemapTiledParams {
   const float* map_y;
   float* out;
   int B, H, W, h, w, Bmap, normalized;
+  const float* lens;  // LENS only: (B,16) = fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, k5, k6, s1, s2, s3, s4
 };
 
-template <int NC, int PAD, bool ALIGN>
-__global__ void __launch_bounds__(256, 4) remap_tiled_kernel(const __grid_constant__ CUtensorMap tmap,
+// distort_points (calibration/distort.py:137-189 without the tilt branch) at pixel (px, py): the operations, their
+// association and the python-scalar products (2 * p1 is formed first, then * x, then * y) of the reference, each
+// rounded on its own as eager torch does.
+__device__ __forceinline__ void lens_distort(const float (&L)[16], float px, float py, float& mx, float& my) {
+  using R = RN<float>;
+  const float fx = L[0], fy = L[1], cx = L[2], cy = L[3];
+  const float x = R::div(R::sub(px, cx), fx), y = R::div(R::sub(py, cy), fy);
+  const float r2 = R::add(R::mul(x, x), R::mul(y, y));
+  const float r4 = R::mul(r2, r2);
+  const float r6 = R::mul(r4, r2);
+  const float num = R::add(R::add(R::add(1.f, R::mul(L[4], r2)), R::mul(L[5], r4)), R::mul(L[8], r6));
+  const float den = R::add(R::add(R::add(1.f, R::mul(L[9], r2)), R::mul(L[10], r4)), R::mul(L[11], r6));
+  const float rad = R::div(num, den);
+  const float xy1 = R::mul(R::mul(R::mul(2.f, L[6]), x), y);                 // 2 * p1 * x * y
+  const float xy2 = R::mul(R::mul(R::mul(2.f, L[7]), x), y);                 // 2 * p2 * x * y
+  const float rx = R::add(r2, R::mul(R::mul(2.f, x), x));                    // r2 + 2 * x * x
+  const float ry = R::add(r2, R::mul(R::mul(2.f, y), y));                    // r2 + 2 * y * y
+  const float xd = R::add(R::add(R::add(R::add(R::mul(x, rad), xy1), R::mul(L[7], rx)), R::mul(L[12], r2)), R::mul(L[13], r4));
+  const float yd = R::add(R::add(R::add(R::add(R::mul(y, rad), R::mul(L[6], ry)), xy2), R::mul(L[14], r2)), R::mul(L[15], r4));
+  mx = R::add(R::mul(fx, xd), cx);
+  my = R::add(R::mul(fy, yd), cy);
+}
+
+template <int NC, int PAD, bool ALIGN, bool LENS = false>
+__global__ void __launch_bounds__(256, LENS ? 3 : 4) remap_tiled_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __grid_constant__ RemapTiledParams p) {
   using R = RN<float>;
   constexpr int TW = 64, TH = 32, BW = 72, BH = 40;
@@ -58,6 +88,11 @@ __global__ void __launch_bounds__(256, 4) remap_tiled_kernel(const __grid_consta
   const float* mxp = p.map_x + (p.Bmap == 1 ? 0 : (size_t)b * oplane);
   const float* myp = p.map_y + (p.Bmap == 1 ? 0 : (size_t)b * oplane);
   const int x0 = tx * TW + lane, y_base = ty * TH + warp * RPW;
+  float L[16];
+  if (LENS) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) L[k] = __ldg(p.lens + (size_t)b * 16 + k);
+  }
 
   // ---- 1. coordinates of this thread's pixels
   float ux[RPW * NJ], uy[RPW * NJ];  // unnormalised, un-padded (what the exact path consumes)
@@ -71,8 +106,12 @@ __global__ void __launch_bounds__(256, 4) remap_tiled_kernel(const __grid_consta
       const int u = i * NJ + j;
       float gx = 0.f, gy = 0.f;
       if (x < p.w && y < p.h) {
-        gx = __ldg(mxp + (size_t)y * p.w + x);
-        gy = __ldg(myp + (size_t)y * p.w + x);
+        if (LENS) {
+          lens_distort(L, (float)x, (float)y, gx, gy);
+        } else {
+          gx = __ldg(mxp + (size_t)y * p.w + x);
+          gy = __ldg(myp + (size_t)y * p.w + x);
+        }
         if (!p.normalized) {
           gx = R::sub(R::mul(fx, gx), 1.f);
           gy = R::sub(R::mul(fy, gy), 1.f);
@@ -187,5 +226,7 @@ __global__ void __launch_bounds__(256, 4) remap_tiled_kernel(const __grid_consta
 
 int remap_tiled_forward(const float* src, const float* map_x, const float* map_y, float* out, int B, int C, int H, int W, int h, int w,
                         int Bmap, int normalized, int interp, int pad, int align, cudaStream_t st);
+// undistort_image in one kernel: bilinear, zeros, align_corners=True, output size = input size; lens (B,16).
+int undistort_tiled_forward(const float* src, const float* lens, float* out, int B, int C, int H, int W, cudaStream_t st);
 
 }  // namespace kb200

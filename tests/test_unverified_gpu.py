@@ -233,3 +233,41 @@ def test_backward_v2_720p_and_goldens(monkeypatch):
             for key, want in outs.items():
                 if key != "cot":
                     assert rel_l2(got[key].cpu(), want) < 1e-4, (name, key)
+
+
+# ------------------------------------------------------------------------------------------ fused undistort_image
+@pytest.mark.parametrize("ncoef", [4, 5, 8, 12, 14])
+@pytest.mark.parametrize("shape", [(2, 3, 64, 128), (1, 1, 70, 132), (3, 3, 270, 480), (1, 3, 1080, 1920)])
+def test_fused_undistort_equals_composition(monkeypatch, ncoef, shape):
+    """kb200_undistort_forward (lens model in registers) == distort_points (torch ops) + remap, bit for bit: the kernel
+    evaluates the reference's op sequence with one rounding per op on the exact integer grid."""
+    KC = K.geometry.calibration
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(ncoef)
+    img = torch.rand(*shape, generator=g).to(DEV)
+    cam = torch.tensor([[0.8 * W, 0.0, 0.5 * W - 3.0], [0.0, 0.75 * W, 0.5 * H + 2.0], [0.0, 0.0, 1.0]]).expand(B, 3, 3).clone()
+    cam[:, 0, 0] += torch.arange(B) * 7.0
+    scale = torch.tensor([0.25, 0.08, 0.003, 0.003, 0.02, 0.05, 0.02, 0.004, 0.003, 0.001, 0.002, 0.0015, 0.0, 0.0])[:ncoef]
+    dist = (torch.rand(B, ncoef, generator=g) - 0.5) * 2 * scale   # tilt terms zero: the fused envelope
+    cam, dist = cam.to(DEV), dist.to(DEV)
+    monkeypatch.delenv("KB200_FUSED_UNDISTORT", raising=False)
+    want = KC.undistort_image(img, cam, dist)
+    before = K._ops.launch_count
+    monkeypatch.setenv("KB200_FUSED_UNDISTORT", "1")
+    got = KC.undistort_image(img, cam, dist)
+    assert K._ops.launch_count == before + 1, "the fused kernel did not run"
+    assert torch.equal(got, want), float((got - want).abs().max())
+
+
+def test_fused_undistort_golden_and_fallbacks(monkeypatch):
+    monkeypatch.setenv("KB200_FUSED_UNDISTORT", "1")
+    KC = K.geometry.calibration
+    WID = golden("wider")
+    for name in WID.names("undistort_image"):   # includes unbatched K, (C,H,W) and 5-D inputs, and the tilted 14-coefficient case
+        op, kw, ins, outs = WID.case(name)
+        got = KC.undistort_image(**{k: v.to(DEV) for k, v in ins.items()})
+        torch.testing.assert_close(got.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
+    img = torch.rand(1, 3, 32, 64, device=DEV, requires_grad=True)
+    cam = torch.tensor([[[50.0, 0, 32], [0, 50.0, 16], [0, 0, 1]]], device=DEV)
+    KC.undistort_image(img, cam, torch.tensor([[0.1, 0.0, 0.0, 0.0]], device=DEV)).sum().backward()   # grad: composition
+    assert img.grad is not None

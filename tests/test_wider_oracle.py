@@ -177,3 +177,46 @@ def test_install_reaches_the_new_callers():
     finally:
         sys.path.remove(stub)
         sys.path.remove("/root/reference")
+
+
+def test_lens_packing_and_kernel_op_order():
+    """The fused undistort kernel (csrc/remap_tiled.cuh:lens_distort) evaluates distort_points from 16 packed numbers.
+    This mirrors its operation tree -- same indices into the packed row, same association, one torch op per device
+    intrinsic -- and must reproduce the oracle's distort_points bit for bit on the exact pixel grid (CPU fp32): it
+    pins the packing order of pack_lens and documents the op order the kernel transcribes."""
+    from kornia_b200.geometry.calibration.undistort import pack_lens
+
+    def lens_distort(L, px, py):
+        fx, fy, cx, cy = L[0], L[1], L[2], L[3]
+        x, y = (px - cx) / fx, (py - cy) / fy
+        r2 = x * x + y * y
+        r4 = r2 * r2
+        r6 = r4 * r2
+        num = ((1.0 + L[4] * r2) + L[5] * r4) + L[8] * r6
+        den = ((1.0 + L[9] * r2) + L[10] * r4) + L[11] * r6
+        rad = num / den
+        xy1 = ((2.0 * L[6]) * x) * y
+        xy2 = ((2.0 * L[7]) * x) * y
+        rx = r2 + (2.0 * x) * x
+        ry = r2 + (2.0 * y) * y
+        xd = (((x * rad + xy1) + L[7] * rx) + L[12] * r2) + L[13] * r4
+        yd = (((y * rad + L[6] * ry) + xy2) + L[14] * r2) + L[15] * r4
+        return fx * xd + cx, fy * yd + cy
+
+    H, W = 45, 64
+    ys, xs = torch.meshgrid(torch.linspace(0, H - 1, H), torch.linspace(0, W - 1, W), indexing="ij")
+    pts = torch.stack([xs, ys], -1).reshape(-1, 2)
+    cam = torch.tensor([[[50.0, 0.0, 31.0], [0.0, 47.0, 22.5], [0.0, 0.0, 1.0]], [[61.0, 0.0, 30.0], [0.0, 60.0, 20.0], [0.0, 0.0, 1.0]]])
+    g = torch.Generator().manual_seed(5)
+    for n in (4, 5, 8, 12, 14):
+        scale = torch.tensor([0.25, 0.08, 0.003, 0.003, 0.02, 0.05, 0.02, 0.004, 0.003, 0.001, 0.002, 0.0015, 0.0, 0.0])[:n]
+        dist = (torch.rand(2, n, generator=g) - 0.5) * 2 * scale
+        lens = pack_lens(cam, dist, pts)
+        assert lens.shape == (2, 16)
+        want = R.distort_points(pts, cam, dist)
+        for b in range(2):
+            mx, my = lens_distort(lens[b], pts[:, 0], pts[:, 1])
+            assert torch.equal(mx, want[b, :, 0]) and torch.equal(my, want[b, :, 1]), n
+    assert pack_lens(cam, torch.tensor([[0.0] * 12 + [0.01, 0.0]] * 2), pts) is None          # tilt: not covered
+    assert pack_lens(cam[0], torch.zeros(4), pts).shape == (1, 16)                             # unbatched K and dist
+    assert pack_lens(cam[:1], torch.zeros(3, 5), pts).shape == (3, 16)                         # broadcast intrinsics

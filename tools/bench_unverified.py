@@ -72,3 +72,6 @@ with torch.no_grad():
     pair("spatial_gradient diff order 2", "KB200_TILED_GRADIENT", lambda: K.filters.spatial_gradient(x, "diff", 2), 16)
     pair("sobel magnitude", "KB200_TILED_GRADIENT", lambda: K.filters.sobel(x), 8)
     pair("pyrdown", "KB200_FUSED_PYRDOWN", lambda: K.geometry.transform.pyrdown(x), 5)
+    cam = torch.tensor([[1500.0, 0.0, 960.0], [0.0, 1500.0, 540.0], [0.0, 0.0, 1.0]], device=dev).expand(B, 3, 3).contiguous()
+    dist = torch.tensor([[-0.2, 0.05, 0.001, -0.002, 0.01]], device=dev).expand(B, 5).contiguous()
+    pair("undistort_image (5 coefficients)", "KB200_FUSED_UNDISTORT", lambda: K.geometry.calibration.undistort_image(x, cam, dist), 8)
