@@ -1,0 +1,84 @@
+// Host emulation shim: lets g++ compile the kernel templates of kornia_b200/csrc/*.cuh as plain C++ so that
+// tools/hostemu/run_emu.cpp can EXECUTE them on the CPU, one fiber per CUDA thread (see hostemu.h, README.md).
+// Force-included before every other header:  g++ -include tools/hostemu/cuda_shim.h ...
+// Nothing here is used by the product build (nvcc never sees KB200_HOST_EMU).
+#pragma once
+#define KB200_HOST_EMU 1
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+// CUDA keywords -> nothing (host_defines.h maps them to attributes gcc does not know)
+#undef __global__
+#undef __device__
+#undef __host__
+#undef __shared__
+#undef __forceinline__
+#undef __noinline__
+#undef __launch_bounds__
+#undef __grid_constant__
+#undef __align__
+#define __global__
+#define __device__
+#define __host__
+#define __shared__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __align__(n) __attribute__((aligned(n)))
+
+// built-in variables: set by the fiber scheduler before a fiber runs
+extern uint3 threadIdx, blockIdx;
+extern dim3 blockDim, gridDim;
+
+using std::max;
+using std::min;
+
+// ---- block-level primitives implemented by the scheduler (hostemu.h)
+void __syncthreads();
+
+// ---- arithmetic intrinsics: compile with -ffp-contract=off so that plain a * b + c is never fused
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline double __dsqrt_rn(double a) { return sqrt(a); }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+inline int __float_as_int(float f) {
+  int i;
+  memcpy(&i, &f, 4);
+  return i;
+}
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+template <typename T>
+inline void __stcs(T* p, T v) { *p = v; }
+inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+inline size_t __cvta_generic_to_global(const void* p) { return (size_t)p; }
+
+// ---- warp-level intrinsics: declared so that the headers parse; the emulator runs threads as independent fibers, so
+// kernels that need lock-step warps (shuffles, votes) are out of its reach and these are never defined
+float __fadd_rd(float, float);
+unsigned __ballot_sync(unsigned, int);
+int __all_sync(unsigned, int);
+void __syncwarp(unsigned = 0xffffffffu);
+template <typename T>
+T __shfl_xor_sync(unsigned, T, int, int = 32);
+template <typename T>
+T __shfl_up_sync(unsigned, T, unsigned, int = 32);
+float atomicAdd(float*, float);
+double atomicAdd(double*, double);
