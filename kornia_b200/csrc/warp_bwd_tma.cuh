@@ -46,10 +46,17 @@ struct BwdStageInfo {
   int soy[TMA_CONSUMER_WARPS];   // strip y origin per consumer warp (>= 0)
 };
 
+#ifdef KB200_HOST_EMU
+static long long emu_exact_path_pixels = 0;
+#endif
+
 // One pixel handled entirely through global memory: exact scatter with bounds tests and, when
 // requested, the coordinate gradient from global taps.  Returns (gix, giy).
 template <int NC, int PAD, bool NEED_SRC, bool NEED_M>
 __device__ __noinline__ float2 bwd_pixel_global(const TmaBwdParams& p, int b, int y, int x, float ix, float iy) {
+#ifdef KB200_HOST_EMU
+  ++emu_exact_path_pixels;  // tools/hostemu reports how many pixels left the shared-memory fast path
+#endif
   const int H = p.H, W = p.W;
   const size_t splane = (size_t)H * W, oplane = (size_t)p.h * p.w;
   const float* gop = p.gout + (size_t)b * NC * oplane + (size_t)y * p.w + x;
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma(const __grid_cons
       }
       if (NEED_SRC) {
         // the previous tile's strip must have been read by the TMA unit before it is cleared
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (lane == 0) tma::bulk_wait_read0();
         __syncwarp();
         float4* z = reinterpret_cast<float4*>(strip_mem);
         for (int e = lane; e < STRIP_FLOATS / 4; e += 32) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -401,10 +408,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma(const __grid_cons
         tma::fence_proxy_async();
         __syncwarp();
         if (lane == 0 && sox < 0x10000000 && soy < 0x10000000 && !(p.debug & 3)) {
-          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmap_gsrc),
-                       "r"(strip_u32), "r"(sox), "r"(soy), "r"(b * NC)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          tma::reduce_add_3d(&tmap_gsrc, strip_u32, sox, soy, b * NC);
+          tma::bulk_commit();
         }
       }
       if (warp == 0) {  // when every warp has released this tile: publish + load the next one
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma(const __grid_cons
       }
     }
   }
-  if (NEED_SRC && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // reductions done before exit
+  if (NEED_SRC && lane == 0) tma::bulk_wait0();  // reductions done before exit
 }
 
 // Second stage of d/dm for the tiled kernel: fixed-order sum over the record rows of each sample.

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
       }
       if (NEED_SRC) {
         // the previous tile's strip must have been read by the TMA unit before it is cleared
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (lane == 0) tma::bulk_wait_read0();
         __syncwarp();
         float4* z = reinterpret_cast<float4*>(strip_mem);
         for (int e = lane; e < STRIP_FLOATS / 4; e += 32) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -275,10 +275,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
         tma::fence_proxy_async();
         __syncwarp();
         if (lane == 0 && sox < 0x10000000 && soy < 0x10000000 && !(p.debug & 3)) {
-          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmap_gsrc),
-                       "r"(strip_u32), "r"(sox), "r"(soy), "r"(b * NC)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          tma::reduce_add_3d(&tmap_gsrc, strip_u32, sox, soy, b * NC);
+          tma::bulk_commit();
         }
       }
       __syncwarp();
@@ -300,7 +298,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
       }
     }
   }
-  if (NEED_SRC && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // reductions done before exit
+  if (NEED_SRC && lane == 0) tma::bulk_wait0();  // reductions done before exit
 }
 
 }  // namespace kb200

@@ -70,15 +70,31 @@ inline void __stcs(T* p, T v) { *p = v; }
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 inline size_t __cvta_generic_to_global(const void* p) { return (size_t)p; }
 
-// ---- warp-level intrinsics: declared so that the headers parse; the emulator runs threads as independent fibers, so
-// kernels that need lock-step warps (shuffles, votes) are out of its reach and these are never defined
+// ---- warp-level intrinsics: rendezvous of the 32 fibers of a warp (hostemu.h).  Every lane of the warp must reach
+// the same sequence of collectives (converged code with the full mask, which is how the kernels use them).
 float __fadd_rd(float, float);
 unsigned __ballot_sync(unsigned, int);
 int __all_sync(unsigned, int);
 void __syncwarp(unsigned = 0xffffffffu);
+unsigned long long emu_warp_exchange(unsigned long long mine, int src_lane);  // deposit, rendezvous, read src_lane's deposit
+int emu_lane();
 template <typename T>
-T __shfl_xor_sync(unsigned, T, int, int = 32);
+inline T __shfl_xor_sync(unsigned, T v, int o, int = 32) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  bits = emu_warp_exchange(bits, emu_lane() ^ o);
+  memcpy(&v, &bits, sizeof(T));
+  return v;
+}
 template <typename T>
-T __shfl_up_sync(unsigned, T, unsigned, int = 32);
+inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) {
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  const int lane = emu_lane();
+  bits = emu_warp_exchange(bits, lane >= (int)d ? lane - (int)d : lane);
+  memcpy(&v, &bits, sizeof(T));
+  return v;
+}
 float atomicAdd(float*, float);
 double atomicAdd(double*, double);

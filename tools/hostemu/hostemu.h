@@ -23,11 +23,23 @@ dim3 blockDim, gridDim;
 
 namespace emu {
 
+struct PendingReduce;
 struct Fiber {
   ucontext_t ctx;
   std::vector<char> stack;
-  bool done = false, at_barrier = false, spinning = false;
+  bool done = false, at_barrier = false, spinning = false, at_wsync = false;
+  unsigned wgen = 0;  // warp collectives completed by this lane
+  unsigned lin = 0;   // linear thread index
   uint3 tid;
+  std::vector<struct PendingReduce> reduces;  // bulk async-groups are per thread
+};
+struct PendingReduce {
+  kb200::tma::EmuMap map;
+  uint32_t src;
+  int c[3];
+};
+struct WarpState {
+  unsigned long long slot[2][32];
 };
 struct PendingTma {
   void* dst;
@@ -42,7 +54,14 @@ static std::function<void()> body;
 static bool lazy_tma = false;
 static std::deque<PendingTma> pending;
 static std::map<uint64_t*, long long> bar_tx;
-static long long n_tma = 0, n_barriers = 0;
+static long long n_tma = 0, n_barriers = 0, n_wsync = 0, n_reduce = 0;
+static std::vector<WarpState> warps;
+static char* smem_base = nullptr;   // the CTA's shared array (set_smem) for 32-bit shared addresses
+static size_t smem_size = 0;
+static void set_smem(void* base, size_t size) {
+  smem_base = static_cast<char*>(base);
+  smem_size = size;
+}
 
 static void fail(const char* what) {
   fprintf(stderr, "hostemu: %s (block %u, thread %u)\n", what, blockIdx.x, cur ? cur->tid.x : 0u);
@@ -82,12 +101,16 @@ static void run_cta(dim3 block, const std::function<void()>& fn) {
   if (fibers.size() < n) fibers.resize(n);
   body = fn;
   blockDim = block;
+  warps.assign((n + 31) / 32, WarpState{});
   pending.clear();
   bar_tx.clear();
   for (unsigned i = 0; i < n; ++i) {
     Fiber& f = fibers[i];
     if (f.stack.empty()) f.stack.resize(512 * 1024);
-    f.done = f.at_barrier = f.spinning = false;
+    f.done = f.at_barrier = f.spinning = f.at_wsync = false;
+    f.wgen = 0;
+    f.lin = i;
+    f.reduces.clear();
     f.tid = make_uint3(i % block.x, (i / block.x) % block.y, i / (block.x * block.y));
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = f.stack.data();
@@ -101,7 +124,7 @@ static void run_cta(dim3 block, const std::function<void()>& fn) {
       Fiber& f = fibers[i];
       if (f.done) continue;
       ++live;
-      if (f.at_barrier) {
+      if (f.at_barrier || f.at_wsync) {
         ++parked;
         continue;
       }
@@ -114,26 +137,45 @@ static void run_cta(dim3 block, const std::function<void()>& fn) {
       else if (f.spinning) ++stuck;
     }
     if (live == 0) break;
+    // warp rendezvous: release every warp whose live lanes have all arrived
+    bool released = false;
+    for (unsigned w = 0; w * 32 < n; ++w) {
+      unsigned wl = 0, wa = 0;
+      for (unsigned i = w * 32; i < std::min(n, w * 32 + 32); ++i) {
+        if (fibers[i].done) continue;
+        ++wl;
+        if (fibers[i].at_wsync) ++wa;
+      }
+      if (wl && wa == wl) {
+        for (unsigned i = w * 32; i < std::min(n, w * 32 + 32); ++i) fibers[i].at_wsync = false;
+        released = true;
+        ++n_wsync;
+      }
+    }
     // recount after the pass
     live = parked = 0;
-    unsigned spinning = 0;
+    unsigned spinning = 0, wparked = 0;
     for (unsigned i = 0; i < n; ++i) {
       if (fibers[i].done) continue;
       ++live;
       if (fibers[i].at_barrier) ++parked;
+      else if (fibers[i].at_wsync) ++wparked;
       else if (fibers[i].spinning) ++spinning;
     }
     if (live == 0) break;
+    if (released) continue;
     if (parked == live) {  // barrier complete
       for (unsigned i = 0; i < n; ++i) fibers[i].at_barrier = false;
       ++n_barriers;
-    } else if (parked + spinning == live) {  // nobody can move: the outstanding loads land now (LAZY), else it is a hang
+    } else if (parked + wparked + spinning == live) {  // nobody can move: the outstanding loads land now (LAZY), else it is a hang
       if (pending.empty()) fail("deadlock: every thread waits on a barrier or an mbarrier and no load is in flight");
       complete(pending.front());
       pending.pop_front();
     }
   }
   if (!pending.empty()) fail("the CTA exited with TMA loads in flight");
+  for (unsigned i = 0; i < n; ++i)
+    if (!fibers[i].reduces.empty()) fail("a thread exited with TMA reduce-adds it never waited for");
   for (auto& kv : bar_tx)
     if (kv.second != 0) fail("the CTA exited with an mbarrier still expecting bytes");
   cur = nullptr;
@@ -177,6 +219,54 @@ void __syncthreads() {
   emu::cur->at_barrier = true;
   emu::yield();
 }
+int emu_lane() { return (int)(emu::cur->lin & 31u); }
+unsigned long long emu_warp_exchange(unsigned long long mine, int src_lane) {
+  emu::Fiber* f = emu::cur;
+  emu::WarpState& w = emu::warps[f->lin >> 5];
+  const unsigned par = f->wgen & 1u;
+  w.slot[par][f->lin & 31u] = mine;
+  f->at_wsync = true;
+  emu::yield();
+  ++f->wgen;
+  return w.slot[par][src_lane & 31];
+}
+void __syncwarp(unsigned) { emu_warp_exchange(0ull, 0); }
+unsigned __ballot_sync(unsigned, int pred) {
+  // every lane needs every deposit: exchange once, then read all slots of that generation
+  emu::Fiber* f = emu::cur;
+  emu::WarpState& w = emu::warps[f->lin >> 5];
+  const unsigned par = f->wgen & 1u;
+  emu_warp_exchange(pred ? 1ull : 0ull, 0);
+  unsigned bits = 0;
+  const unsigned base = (f->lin >> 5) * 32, n = blockDim.x * blockDim.y * blockDim.z;
+  for (unsigned l = 0; l < 32 && base + l < n; ++l)
+    if (w.slot[par][l]) bits |= 1u << l;
+  return bits;
+}
+int __all_sync(unsigned m, int pred) {
+  const unsigned base = (emu::cur->lin >> 5) * 32, n = blockDim.x * blockDim.y * blockDim.z;
+  const unsigned lanes = std::min(32u, n - base);
+  return __ballot_sync(m, pred) == (lanes == 32 ? 0xffffffffu : ((1u << lanes) - 1));
+}
+#include <cfenv>
+float __fadd_rd(float a, float b) {
+  const int old = fegetround();
+  fesetround(FE_DOWNWARD);
+  volatile float va = a, vb = b;
+  volatile float r = va + vb;
+  fesetround(old);
+  return r;
+}
+float atomicAdd(float* p, float v) {
+  const float old = *p;
+  *p = old + v;
+  return old;
+}
+double atomicAdd(double* p, double v) {
+  const double old = *p;
+  *p = old + v;
+  return old;
+}
 namespace kb200 {
 namespace tma {
 void emu_spin() {
@@ -184,6 +274,41 @@ void emu_spin() {
   emu::yield();
 }
 long long& emu_bar_tx(uint64_t* bar) { return emu::bar_tx[bar]; }
+uint32_t emu_smem_addr(const void* p) {
+  const char* c = static_cast<const char*>(p);
+  if (!emu::smem_base || c < emu::smem_base || c >= emu::smem_base + emu::smem_size) emu::fail("smem_u32 of a pointer outside the CTA's shared array");
+  return (uint32_t)(c - emu::smem_base) + 0x10000u;
+}
+float* emu_smem_ptr(uint32_t addr) {
+  const uint32_t off = addr - 0x10000u;
+  if (off >= emu::smem_size || (off & 3u)) emu::fail("ld/st.shared outside the CTA's shared array (or misaligned)");
+  return reinterpret_cast<float*>(emu::smem_base + off);
+}
+static void emu_reduce_complete(const emu::PendingReduce& r) {
+  const auto& m = r.map;
+  if (r.c[0] < 0 || r.c[1] < 0 || r.c[2] < 0) emu::fail("TMA reduce with a negative coordinate (traps on B200: tools/tma_reduce_probe.cu)");
+  if (((long long)r.c[0] * 4) % 16 != 0) emu::fail("TMA reduce: innermost coordinate not 16-byte aligned");
+  const float* src = emu_smem_ptr(r.src);
+  if (((size_t)src & 127) != 0) emu::fail("TMA reduce: shared-memory source not 128-byte aligned");
+  for (uint32_t z = 0; z < m.box[2]; ++z)
+    for (uint32_t y = 0; y < m.box[1]; ++y)
+      for (uint32_t x = 0; x < m.box[0]; ++x) {
+        const long long gx = (long long)r.c[0] + x, gy = (long long)r.c[1] + y, gz = (long long)r.c[2] + z;
+        if (gx >= (long long)m.dims[0] || gy >= (long long)m.dims[1] || gz >= (long long)m.dims[2]) continue;  // clipped
+        float* g = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(m.base)) + gz * m.strides[1] + gy * m.strides[0] + gx * 4);
+        *g += src[((size_t)z * m.box[1] + y) * m.box[0] + x];
+      }
+  ++emu::n_reduce;
+}
+void emu_reduce_add_issue(const EmuMap* map, uint32_t src_smem, int c0, int c1, int c2) {
+  emu::PendingReduce r{*map, src_smem, {c0, c1, c2}};
+  if (emu::lazy_tma) emu::cur->reduces.push_back(r);  // reads the strip as late as the kernel allows: at its wait_group
+  else emu_reduce_complete(r);
+}
+void emu_bulk_wait(bool) {
+  for (const auto& r : emu::cur->reduces) emu_reduce_complete(r);
+  emu::cur->reduces.clear();
+}
 void emu_tma_issue(void* dst, const EmuMap* map, uint64_t* bar, int c0, int c1, int c2) {
   if (((long long)c0 * 4) % 16 != 0) emu::fail("TMA: innermost coordinate not 16-byte aligned (traps on B200)");
   if (((size_t)dst & 127) != 0) emu::fail("TMA: shared-memory destination not 128-byte aligned");

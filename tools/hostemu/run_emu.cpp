@@ -14,6 +14,8 @@
 #include "../../kornia_b200/csrc/gradient_tiled.cuh"
 #include "../../kornia_b200/csrc/sepfilter_vwalk.cuh"
 #include "../../kornia_b200/csrc/ssim_vwalk.cuh"
+#include "../../kornia_b200/csrc/remap_tiled.cuh"
+#include "../../kornia_b200/csrc/warp_bwd_tma2.cuh"
 
 #include <random>
 #include <string>
@@ -25,6 +27,9 @@ alignas(128) unsigned char f2d_smem[256 * 1024];
 alignas(128) unsigned char gradt_smem[256 * 1024];
 alignas(128) unsigned char ssimv_smem[256 * 1024];
 alignas(128) float ssim_smem[64 * 1024];
+alignas(128) unsigned char remap_smem[256 * 1024];
+alignas(128) unsigned char bwd_smem[256 * 1024];
+alignas(128) unsigned char bwd2_smem[256 * 1024];
 void set_error(const char*, ...) {}
 }  // namespace kb200
 
@@ -234,6 +239,187 @@ static void test_ssim(int planes, int H, int W, unsigned grid, bool lazy) {
   compare("ssim_vwalk_kernel vs ssim_tiled_kernel " + tag, o2, o1, n);
 }
 
+
+// ------------------------------------------------------------------------------------------ remap / fused undistort
+static float ref_remap_pixel(const float* plane, int H, int W, float mx, float my) {
+  // conversions.py:1487-1498 (normalise), GridSampler.h:27-35 (unnormalise, align_corners=True), bilinear + zeros
+  const float Wm1 = (float)(W - 1), Hm1 = (float)(H - 1);
+  const float fx = 2.f / fmaxf(Wm1, 1e-8f), fy = 2.f / fmaxf(Hm1, 1e-8f);
+  const float gx = fx * mx - 1.f, gy = fy * my - 1.f;
+  const float ix = ((gx + 1.f) * 0.5f) * Wm1, iy = ((gy + 1.f) * 0.5f) * Hm1;
+  if (!(fabsf(ix) < 4.0e6f && fabsf(iy) < 4.0e6f)) return 0.f;
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float wx1 = (x0f + 1.f) - ix, wx0 = ix - x0f, wy1 = (y0f + 1.f) - iy, wy0 = iy - y0f;
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  auto tap = [&](int y, int x) { return (y >= 0 && y < H && x >= 0 && x < W) ? plane[(size_t)y * W + x] : 0.f; };
+  float a = fmaf(tap(y0, x0), wx1 * wy1, 0.f);
+  a = fmaf(tap(y0, x0 + 1), wx0 * wy1, a);
+  a = fmaf(tap(y0 + 1, x0), wx1 * wy0, a);
+  a = fmaf(tap(y0 + 1, x0 + 1), wx0 * wy0, a);
+  return a;
+}
+
+static void test_undistort(int B, int H, int W, bool lazy) {
+  emu::lazy_tma = lazy;
+  emu::set_smem(remap_smem, sizeof(remap_smem));
+  constexpr int C = 3;
+  std::vector<float> ss, o1s, o2s, mxs, mys;
+  const size_t n = (size_t)B * C * H * W, npix = (size_t)B * H * W;
+  float* src = aligned(ss, n);
+  for (size_t i = 0; i < n; ++i) src[i] = randv(1)[0];
+  std::vector<float> lens((size_t)B * 16);
+  for (int b = 0; b < B; ++b) {
+    const float L[16] = {0.8f * W + 3 * b, 0.75f * W, 0.5f * W - 3.f, 0.5f * H + 2.f, -0.21f, 0.07f, 0.002f, -0.003f, 0.01f, 0.04f, -0.02f, 0.004f, 0.003f, -0.001f, 0.002f, 0.0015f};
+    memcpy(&lens[(size_t)b * 16], L, sizeof(L));
+  }
+  // the maps the host composition would hand to remap: lens_distort on the exact integer grid (the same device function)
+  float* mx = aligned(mxs, npix);
+  float* my = aligned(mys, npix);
+  std::vector<float> want(n);
+  for (int b = 0; b < B; ++b) {
+    float L[16];
+    memcpy(L, &lens[(size_t)b * 16], sizeof(L));
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        float a, c;
+        lens_distort(L, (float)x, (float)y, a, c);
+        mx[((size_t)b * H + y) * W + x] = a;
+        my[((size_t)b * H + y) * W + x] = c;
+        for (int ch = 0; ch < C; ++ch)
+          want[(((size_t)b * C + ch) * H + y) * W + x] = ref_remap_pixel(src + ((size_t)b * C + ch) * H * W, H, W, a, c);
+      }
+  }
+  const CUtensorMap map = emu::make_map(src, W, H, B * C, 72, 40, C);
+  const dim3 grid(ceil_div(W, 64), ceil_div(H, 32), B);
+  const std::string tag = std::to_string(B) + "x3x" + std::to_string(H) + "x" + std::to_string(W) + (lazy ? " lazy" : " eager");
+  float* o1 = aligned(o1s, n);
+  {
+    RemapTiledParams p{src, mx, my, o1, B, H, W, H, W, B, 0, nullptr};
+    emu::launch3(grid, dim3(256), [&] { remap_tiled_kernel<3, KB200_ZEROS, true, false>(map, p); });
+    compare("remap_tiled_kernel (verified on hw) vs scalar bilinear " + tag, o1, want.data(), n);
+  }
+  float* o2 = aligned(o2s, n);
+  {
+    RemapTiledParams p{src, nullptr, nullptr, o2, B, H, W, H, W, B, 0, lens.data()};
+    emu::launch3(grid, dim3(256), [&] { remap_tiled_kernel<3, KB200_ZEROS, true, true>(map, p); });
+    compare("remap_tiled_kernel<LENS> (fused undistort) vs maps + remap " + tag, o2, o1, n);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ tiled warp backward
+template <bool PROJ>
+static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool lazy, bool tame = false) {
+  emu::lazy_tma = lazy;
+  constexpr int C = 3;
+  constexpr bool ALIGN = true;
+  const size_t ns = (size_t)B * C * H * W, no = (size_t)B * C * h * w;
+  std::vector<float> ss, gs, g1s, g2s;
+  float* src = aligned(ss, ns);
+  float* gout = aligned(gs, no);
+  for (size_t i = 0; i < ns; ++i) src[i] = randv(1)[0];
+  for (size_t i = 0; i < no; ++i) gout[i] = randv(1, -0.5f, 0.5f)[0];
+  std::vector<float> m((size_t)B * 9), bx(w), by(h);
+  for (int i = 0; i < w; ++i) bx[i] = ((float)i / (float)(w - 1) - 0.5f) * 2.f;
+  for (int i = 0; i < h; ++i) by[i] = ((float)i / (float)(h - 1) - 0.5f) * 2.f;
+  for (int b = 0; b < B; ++b) {  // normalised src <- dst maps: near identity, a shift out of view, a 25 degree rotation
+    // tame: the headline's kind of map (a few pixels of jitter): almost every pixel on the shared-memory fast path
+    const float t = tame ? 0.004f * (b - 1) : (b == 2 ? 0.436f : 0.02f * b);
+    const float M[9] = {cosf(t) * (1.f + (tame ? 0.004f : 0.03f) * b), -sinf(t), (tame ? 0.01f : 0.05f) * b - (!tame && b == 1 ? 0.7f : 0.f), sinf(t),
+                        cosf(t) * (tame ? 0.995f : 0.97f), tame ? -0.008f : -0.03f, PROJ ? (tame ? 0.004f : 0.02f) : 0.f, PROJ ? (tame ? -0.003f : -0.015f) : 0.f, 1.f};
+    memcpy(&m[(size_t)b * 9], M, sizeof(M));
+  }
+  // scalar reference in double (same fp32 coordinate chain through the kernels' own helpers)
+  std::vector<double> gsrc_ref(ns, 0.0), gm_ref((size_t)B * 9, 0.0);
+  const float Wm1 = (float)(W - 1), Hm1 = (float)(H - 1);
+  for (int b = 0; b < B; ++b) {
+    Mat3<float> mm;
+    mm.load(&m[(size_t)b * 9]);
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        float gx, gy, den;
+        map_point<float, PROJ>(mm, bx[x], by[y], gx, gy, den);
+        const float ix = unnorm<ALIGN>(gx, Wm1, (float)W), iy = unnorm<ALIGN>(gy, Hm1, (float)H);
+        if (!(fabsf(ix) < 1.0e9f && fabsf(iy) < 1.0e9f)) continue;
+        const float x0f = floorf(ix), y0f = floorf(iy);
+        const double wx1 = (double)((x0f + 1.f) - ix), wx0 = (double)(ix - x0f), wy1 = (double)((y0f + 1.f) - iy), wy0 = (double)(iy - y0f);
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        double gix = 0, giy = 0;
+        for (int c = 0; c < C; ++c) {
+          const double go = gout[(((size_t)b * C + c) * h + y) * w + x];
+          const float* sp = src + ((size_t)b * C + c) * H * W;
+          double* gp = gsrc_ref.data() + ((size_t)b * C + c) * H * W;
+          auto ok = [&](int yy, int xx) { return yy >= 0 && yy < H && xx >= 0 && xx < W; };
+          auto v = [&](int yy, int xx) { return ok(yy, xx) ? (double)sp[(size_t)yy * W + xx] : 0.0; };
+          if (ok(y0, x0)) gp[(size_t)y0 * W + x0] += wx1 * wy1 * go;
+          if (ok(y0, x0 + 1)) gp[(size_t)y0 * W + x0 + 1] += wx0 * wy1 * go;
+          if (ok(y0 + 1, x0)) gp[(size_t)(y0 + 1) * W + x0] += wx1 * wy0 * go;
+          if (ok(y0 + 1, x0 + 1)) gp[(size_t)(y0 + 1) * W + x0 + 1] += wx0 * wy0 * go;
+          gix += go * ((v(y0, x0 + 1) - v(y0, x0)) * wy1 + (v(y0 + 1, x0 + 1) - v(y0 + 1, x0)) * wy0);
+          giy += go * ((v(y0 + 1, x0) - v(y0, x0)) * wx1 + (v(y0 + 1, x0 + 1) - v(y0, x0 + 1)) * wx0);
+        }
+        const double rden = PROJ ? 1.0 / (double)den : 1.0;
+        const double ax = gix * (Wm1 * 0.5) * rden, ay = giy * (Hm1 * 0.5) * rden, az = -(ax * gx + ay * gy);
+        double* g = &gm_ref[(size_t)b * 9];
+        g[0] += ax * bx[x]; g[1] += ax * by[y]; g[2] += ax;
+        g[3] += ay * bx[x]; g[4] += ay * by[y]; g[5] += ay;
+        if (PROJ) { g[6] += az * bx[x]; g[7] += az * by[y]; g[8] += az; }
+      }
+  }
+  const int nstrips = B * ceil_div(h, 32), max_segs = nstrips / (int)grid + 2;
+  const size_t rows = (size_t)grid * max_segs;
+  long long exact[3] = {0, 0, 0};
+  auto run = [&](int version, float* gsrc, std::vector<double>& gm) {
+    emu_exact_path_pixels = 0;
+    for (size_t i = 0; i < ns; ++i) gsrc[i] = 0.f;
+    std::vector<float> records(rows * 8 * 9, 0.f);
+    std::vector<int> rb(rows, -7);
+    TmaBwdParams p{};
+    p.gout = gout; p.src = src; p.m = m.data(); p.bx = bx.data(); p.by = by.data(); p.gsrc = gsrc;
+    p.records = records.data(); p.record_batch = rb.data();
+    p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.max_segs = max_segs; p.debug = 0;
+    const CUtensorMap mgsrc = emu::make_map(gsrc, W, H, B * C, 72, BWD_SH, C), mgout = emu::make_map(gout, w, h, B * C, 64, 32, C);
+    if (version == 1) {
+      emu::set_smem(bwd_smem, sizeof(bwd_smem));
+      const CUtensorMap msrc = emu::make_map(src, W, H, B * C, 72, 40, C);
+      emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma<C, KB200_ZEROS, PROJ, ALIGN, true, true>(msrc, mgsrc, mgout, p); });
+    } else {
+      emu::set_smem(bwd2_smem, sizeof(bwd2_smem));
+      const CUtensorMap mwin = emu::make_map(src, W, H, B * C, 72, BWD_SH, C);
+      emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true>(mwin, mgsrc, mgout, p); });
+    }
+    exact[version] = emu_exact_path_pixels;
+    gm.assign((size_t)B * 9, 0.0);
+    for (size_t r = 0; r < rows; ++r)
+      if (rb[r] >= 0)
+        for (int wv = 0; wv < 8; ++wv)
+          for (int k = 0; k < 9; ++k) gm[(size_t)rb[r] * 9 + k] += (double)records[(r * 8 + wv) * 9 + k];
+  };
+  const std::string tag = std::string(PROJ ? "projective " : "affine     ") + std::to_string(B) + "x3x" + std::to_string(H) + "x" + std::to_string(W) + " -> " +
+                          std::to_string(h) + "x" + std::to_string(w) + " grid=" + std::to_string(grid) + (lazy ? " lazy" : " eager");
+  float* g1 = aligned(g1s, ns);
+  float* g2 = aligned(g2s, ns);
+  std::vector<double> gm1, gm2;
+  run(1, g1, gm1);
+  run(2, g2, gm2);
+  auto check = [&](const char* name, const float* g, const std::vector<double>& gm) {
+    double num = 0, den = 0, worst = 0;
+    for (size_t i = 0; i < ns; ++i) {
+      const double d = (double)g[i] - gsrc_ref[i];
+      num += d * d; den += gsrc_ref[i] * gsrc_ref[i];
+      worst = std::max(worst, fabs(d));
+    }
+    double mn = 0, md = 0;
+    for (size_t i = 0; i < gm.size(); ++i) { mn += (gm[i] - gm_ref[i]) * (gm[i] - gm_ref[i]); md += gm_ref[i] * gm_ref[i]; }
+    const double e_src = sqrt(num / den), e_m = sqrt(mn / md);
+    const bool ok = e_src < 2e-6 && worst < 2e-5 && e_m < 1e-4;
+    printf("%s %-58s %s  d/dsrc rel-L2 %.2e max-abs %.2e, d/dM rel-L2 %.2e\n", ok ? "ok  " : "FAIL", name, tag.c_str(), e_src, worst, e_m);
+    if (!ok) ++failures;
+  };
+  printf("     pixels on the exact (global-memory) path: warp_bwd_tma %lld, warp_bwd_tma2 %lld of %d\n", exact[1], exact[2], B * h * w);
+  check("warp_bwd_tma (verified on hw) vs fp64 scalar backward", g1, gm1);
+  check("warp_bwd_tma2 (per-warp pipelines) vs fp64 scalar backward", g2, gm2);
+}
+
 int main() {
   for (int lazy = 0; lazy < 2; ++lazy) {
     // grids that do not divide the number of strips / bands: segments that start in the middle of a band
@@ -256,8 +442,15 @@ int main() {
     test_ssim<3>(1, 32, 64, 1, lazy);
     test_ssim<7>(2, 97, 260, 7, lazy);
     test_ssim<9>(1, 6, 8, 1, lazy);
+    test_undistort(2, 70, 132, lazy);
+    test_undistort(1, 33, 64, lazy);
+    test_backward<true>(3, 70, 132, 70, 132, 2, lazy);
+    test_backward<false>(3, 64, 128, 50, 96, 3, lazy);
+    test_backward<true>(3, 40, 72, 66, 132, 4, lazy);
+    test_backward<true>(3, 96, 200, 96, 200, 3, lazy, true);
+    test_backward<false>(2, 70, 132, 70, 132, 5, lazy, true);
   }
-  printf("%s: %d failing comparisons, %lld TMA loads and %lld CTA barriers emulated\n", failures ? "FAILED" : "PASSED", failures, emu::n_tma,
-         emu::n_barriers);
+  printf("%s: %d failing comparisons, %lld TMA loads, %lld TMA reduce-adds, %lld CTA barriers and %lld warp rendezvous emulated\n",
+         failures ? "FAILED" : "PASSED", failures, emu::n_tma, emu::n_reduce, emu::n_barriers, emu::n_wsync);
   return failures ? 1 : 0;
 }

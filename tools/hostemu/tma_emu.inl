@@ -17,7 +17,11 @@ void emu_tma_issue(void* dst, const EmuMap* map, uint64_t* bar, int c0, int c1, 
 void emu_spin();                                                                            // yield while polling
 long long& emu_bar_tx(uint64_t* bar);                                                       // outstanding bytes of a barrier
 
-inline uint32_t smem_u32(const void* p) { return (uint32_t)(size_t)p; }
+// 32-bit shared-memory addresses: offsets into the CTA's shared array (emu_set_smem), so that the kernels' modular
+// address arithmetic works and every ld/st.shared is bounds-checked
+uint32_t emu_smem_addr(const void* p);
+float* emu_smem_ptr(uint32_t addr);
+inline uint32_t smem_u32(const void* p) { return emu_smem_addr(p); }
 inline void mbar_init(uint64_t* bar, uint32_t count) {
   EmuBar b{0u, (int16_t)count, (int16_t)count};
   memcpy(bar, &b, 8);
@@ -48,9 +52,21 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 inline void load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   emu_tma_issue(dst, reinterpret_cast<const EmuMap*>(map), bar, c0, c1, c2);
 }
-inline float lds(uint32_t) { abort(); }
-inline float lds_ro(uint32_t) { abort(); }
-inline void sts(uint32_t, float) { abort(); }
-inline bool elect_one() { abort(); }
+inline float lds(uint32_t a) { return *emu_smem_ptr(a); }
+inline float lds_ro(uint32_t a) { return *emu_smem_ptr(a); }
+inline void sts(uint32_t a, float v) { *emu_smem_ptr(a) = v; }
+inline bool elect_one() {  // elect.sync: a warp collective that picks one lane
+  emu_warp_exchange(0ull, emu_lane());
+  return emu_lane() == 0;
+}
+void emu_reduce_add_issue(const EmuMap* map, uint32_t src_smem, int c0, int c1, int c2);
+void emu_bulk_wait(bool read_only);
+inline void reduce_add_3d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2) {
+  emu_reduce_add_issue(reinterpret_cast<const EmuMap*>(map), src_smem, c0, c1, c2);
+}
+inline void bulk_commit() {}
+inline void bulk_wait_read0() { emu_bulk_wait(true); }
+inline void bulk_wait0() { emu_bulk_wait(false); }
+inline float rcp_approx(float den) { return 1.0f / den; }  // any approximation within the refinement's basin gives the same quotients
 inline void prefetch_3d(const CUtensorMap*, int, int, int) {}
 inline void prefetch_map(const CUtensorMap*) {}
