@@ -546,6 +546,9 @@ int kb200_sepfilter_lerp_forward(const void* x, const void* kernel_x, const void
     return KB200_EUNSUPPORTED;
   }
   const float w = (float)weight;
+  rc = sepfilter_vwalk_forward((const float*)x, (const float*)kernel_x, (const float*)kernel_y, (float*)out, B, C, H, W, Bkx, kw, Bky, kh,
+                               border, same, (cudaStream_t)stream, &w);  // opt-in (KB200_SEP_VWALK=1), declines otherwise
+  if (rc != KB200_EUNSUPPORTED) return rc;
   rc = sepfilter_tiled_forward((const float*)x, (const float*)kernel_x, (const float*)kernel_y, (float*)out, B, C, H, W, Bkx, kw, Bky,
                                kh, border, same, (cudaStream_t)stream, &w);
   if (rc == KB200_EUNSUPPORTED) set_error("the fused filter + lerp kernel covers square odd kernels up to 11 taps, 'same', non-circular borders");

@@ -3,10 +3,10 @@
 
 namespace kb200 {
 
-template <int K, int BORDER>
+template <int K, int BORDER, bool LERP = false>
 static int launch_sep_vwalk(const CUtensorMap& map_main, const CUtensorMap& map_pro, const SepTiledParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)(2 * SEPT_TH * SEPT_BW + (SEPT_TH + K - 1) * SEPT_TW) * 4 + 2 * sizeof(uint64_t);
-  auto kern = sepfilter_vwalk_kernel<K, BORDER>;
+  auto kern = sepfilter_vwalk_kernel<K, BORDER, LERP>;
   static unsigned long long configured = 0;  // per instantiation, one bit per device
   if (first_use_on_device(configured)) {
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -24,7 +24,7 @@ static int launch_sep_vwalk(const CUtensorMap& map_main, const CUtensorMap& map_
 }
 
 int sepfilter_vwalk_forward(const float* x, const float* kx, const float* ky, float* out, int B, int C, int H, int W, int Bkx, int kw,
-                            int Bky, int kh, int border, int same, cudaStream_t st) {
+                            int Bky, int kh, int border, int same, cudaStream_t st, const float* lerp_w) {
   const char* on = getenv("KB200_SEP_VWALK");  // off by default: not yet run on hardware
   if (!(on && on[0] == '1')) return KB200_EUNSUPPORTED;
   if (!same || kw != kh || (kw & 1) == 0 || kw < 3 || kw > 17 || border == KB200_CIRCULAR) return KB200_EUNSUPPORTED;
@@ -46,7 +46,23 @@ int sepfilter_vwalk_forward(const float* x, const float* kx, const float* ky, fl
   if (encode(&map_pro, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box_pro, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return KB200_EUNSUPPORTED;
-  SepTiledParams p{kx, ky, out, C, H, W, Bkx, Bky, B * C, x, 0.f};
+  SepTiledParams p{kx, ky, out, C, H, W, Bkx, Bky, B * C, x, lerp_w ? *lerp_w : 0.f};
+  if (lerp_w) {  // unsharp_mask: the same envelope as the strip-walking lerp kernel
+    if (kw > 11 || (reinterpret_cast<uintptr_t>(x) & 7) != 0) return KB200_EUNSUPPORTED;
+#define KB_SEPV_LERP_CASE(K_)                                                                                  \
+  if (kw == K_) {                                                                                              \
+    if (border == KB200_CONSTANT) return launch_sep_vwalk<K_, KB200_CONSTANT, true>(map_main, map_pro, p, st); \
+    if (border == KB200_REFLECT) return launch_sep_vwalk<K_, KB200_REFLECT, true>(map_main, map_pro, p, st);   \
+    return launch_sep_vwalk<K_, KB200_REPLICATE, true>(map_main, map_pro, p, st);                              \
+  }
+    KB_SEPV_LERP_CASE(3)
+    KB_SEPV_LERP_CASE(5)
+    KB_SEPV_LERP_CASE(7)
+    KB_SEPV_LERP_CASE(9)
+    KB_SEPV_LERP_CASE(11)
+#undef KB_SEPV_LERP_CASE
+    return KB200_EUNSUPPORTED;
+  }
 #define KB_SEPV_CASE(K_)                                                                              \
   if (kw == K_) {                                                                                     \
     if (border == KB200_CONSTANT) return launch_sep_vwalk<K_, KB200_CONSTANT>(map_main, map_pro, p, st); \

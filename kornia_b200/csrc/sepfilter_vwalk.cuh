@@ -24,7 +24,8 @@
 
 namespace kb200 {
 
-template <int K, int BORDER>
+// LERP: out = lerp(filtered, x, w) in the epilogue (unsharp_mask), as in sepfilter_tiled_kernel<K, BORDER, true>.
+template <int K, int BORDER, bool LERP = false>
 __global__ void __launch_bounds__(256, 3) sepfilter_vwalk_kernel(const __grid_constant__ CUtensorMap tmap_main,
                                                                  const __grid_constant__ CUtensorMap tmap_pro,
                                                                  const __grid_constant__ SepTiledParams p) {
@@ -191,6 +192,16 @@ __global__ void __launch_bounds__(256, 3) sepfilter_vwalk_kernel(const __grid_co
           }
         }
         float* orow = p.out + (size_t)plane * p.H * p.W + (size_t)(y0 + yb * RY) * p.W + (size_t)x0 + 2 * cp;
+        if (LERP) {
+          const float* xin = p.x + (orow - p.out);
+#pragma unroll
+          for (int o = 0; o < RY; ++o) {
+            if (y0 + yb * RY + o < p.H && x0 + 2 * cp < p.W) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(xin + (size_t)o * p.W));
+              acc[o] = make_float2(lerp_like_torch(acc[o].x, v.x, p.lerp_w), lerp_like_torch(acc[o].y, v.y, p.lerp_w));
+            }
+          }
+        }
         if (y0 + TH <= p.H && cols_full) {
 #pragma unroll
           for (int o = 0; o < RY; ++o) {

@@ -24,3 +24,14 @@ def test_kernels_on_the_host_emulator():
                    "remap_tiled_kernel<LENS>", "warp_bwd_tma (verified on hw)", "warp_bwd_tma2"):
         assert kernel in run.stdout, kernel
     assert "FAIL" not in run.stdout, tail
+
+
+@pytest.mark.skipif(shutil.which("g++") is None or shutil.which("make") is None or not os.path.exists("/usr/local/cuda/include/cuda.h"),
+                    reason="needs g++, make and the CUDA headers")
+def test_filter_kernels_on_random_shapes():
+    """300 random (kernel, border, shape, grid, completion mode) draws: images smaller than a tile, one-row last tiles,
+    more CTAs than bands, segments that start inside a band."""
+    build = subprocess.run(["make", "-C", EMU], capture_output=True, text=True, timeout=600)
+    assert build.returncode == 0, build.stdout[-2000:] + build.stderr[-4000:]
+    run = subprocess.run([os.path.join(EMU, "run_emu"), "--fuzz", "300"], capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0 and "PASSED: 0 failing comparisons" in run.stdout and "FAIL " not in run.stdout, run.stdout[-3000:] + run.stderr[-2000:]

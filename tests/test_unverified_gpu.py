@@ -107,6 +107,18 @@ def test_band_walk_separable_filter_bit_identical(monkeypatch, border, ksize, sh
     assert torch.equal(got, want), float((got - want).abs().max())
 
 
+@pytest.mark.parametrize("border", ["reflect", "replicate", "constant"])
+@pytest.mark.parametrize("ksize,shape", [(3, (2, 3, 70, 132)), (5, (1, 1, 32, 128)), (11, (1, 2, 97, 260)), (7, (2, 3, 1080, 1920))])
+def test_band_walk_unsharp_mask_bit_identical(monkeypatch, border, ksize, shape):
+    """unsharp_mask through the lerp epilogue of the band-walking kernel == through the strip-walking one."""
+    x = torch.rand(*shape, device=DEV)
+    monkeypatch.delenv("KB200_SEP_VWALK", raising=False)
+    want = K.filters.unsharp_mask(x, (ksize, ksize), (1.5, 1.5), border)
+    monkeypatch.setenv("KB200_SEP_VWALK", "1")
+    got = K.filters.unsharp_mask(x, (ksize, ksize), (1.5, 1.5), border)
+    assert torch.equal(got, want), float((got - want).abs().max())
+
+
 def test_band_walk_many_segments_and_blur_golden(monkeypatch):
     """More bands than CTAs (leftover bands are cut into runs: segments that start in the middle of a band), and the
     gaussian_blur2d goldens of the reference through the new kernel."""

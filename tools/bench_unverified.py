@@ -65,6 +65,7 @@ with torch.no_grad():
     pair("gaussian_blur2d k=11 (cfg3)", "KB200_SEP_VWALK", lambda: K.gaussian_blur2d(x, (11, 11), (2.0, 2.0)), 8)
     pair("gaussian_blur2d k=5", "KB200_SEP_VWALK", lambda: K.gaussian_blur2d(x, (5, 5), (1.0, 1.0)), 8)
     pair("gaussian_blur2d k=17", "KB200_SEP_VWALK", lambda: K.gaussian_blur2d(x, (17, 17), (3.0, 3.0)), 8)
+    pair("unsharp_mask 5x5", "KB200_SEP_VWALK", lambda: K.filters.unsharp_mask(x, (5, 5), (1.5, 1.5)), 8)
     pair("ssim window 11", "KB200_SSIM_VWALK", lambda: K.metrics.ssim(x, y, 11), 12)
     pair("ssim window 5", "KB200_SSIM_VWALK", lambda: K.metrics.ssim(x, y, 5), 12)
     pair("spatial_gradient sobel order 1", "KB200_TILED_GRADIENT", lambda: K.filters.spatial_gradient(x, "sobel", 1), 12)

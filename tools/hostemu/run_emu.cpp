@@ -122,6 +122,16 @@ static void test_sepfilter(int B, int C, int H, int W, unsigned grid, bool lazy)
     emu::launch(grid, dim3(256), [&] { sepfilter_vwalk_kernel<K, BORDER>(main, pro, p); });
     compare("sepfilter_vwalk_kernel                  " + tag, o2, want.data(), want.size());
   }
+  if (K <= 11) {  // unsharp_mask epilogue: both lerp kernels against each other (|w| < 0.5 and >= 0.5 take different forms)
+    const float wts[2] = {0.3f, 2.0f};
+    const float wt = wts[(H + W) & 1];
+    const CUtensorMap map = emu::make_map(x, W, H, planes, SEPT_BW, SEPT_TH + K - 1, 1);
+    const CUtensorMap main = emu::make_map(x, W, H, planes, SEPT_BW, SEPT_TH, 1), pro = emu::make_map(x, W, H, planes, SEPT_BW, K - 1, 1);
+    SepTiledParams p1{kx.data(), ky.data(), o1, C, H, W, B, 1, planes, x, wt}, p2{kx.data(), ky.data(), o2, C, H, W, B, 1, planes, x, wt};
+    emu::launch(grid, dim3(256), [&] { sepfilter_tiled_kernel<K, BORDER, true>(map, p1); });
+    emu::launch(grid, dim3(256), [&] { sepfilter_vwalk_kernel<K, BORDER, true>(main, pro, p2); });
+    compare("sepfilter_vwalk_kernel<LERP> vs tiled<LERP>  " + tag, o2, o1, want.size());
+  }
 }
 
 // ------------------------------------------------------------------------------------------ filter2d / pyrdown / derivatives
@@ -420,7 +430,35 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
   check("warp_bwd_tma2 (per-warp pipelines) vs fp64 scalar backward", g2, gm2);
 }
 
-int main() {
+// Random shapes, grids and completion modes (run_emu --fuzz N): shakes out the edge cases the fixed list does not name
+// -- images smaller than a tile, one-row last tiles, bands narrower than the halo, more CTAs than strips.
+static void fuzz(int rounds) {
+  std::mt19937 g(20260923);
+  auto pick = [&](int lo, int hi) { return lo + (int)(g() % (unsigned)(hi - lo + 1)); };
+  for (int r = 0; r < rounds; ++r) {
+    const int H = pick(1, 110), W = 4 * pick(1, 70), planes = pick(1, 4), lazy = pick(0, 1);
+    const unsigned grid = (unsigned)pick(1, 9);
+    switch (pick(0, 9)) {
+      case 0: if (H > 5 && W > 5) test_sepfilter<11, KB200_REFLECT>(1, planes, H, W, grid, lazy); break;
+      case 1: if (H > 8 && W > 8) test_sepfilter<17, KB200_REPLICATE>(1, planes, H, W, grid, lazy); break;
+      case 2: test_sepfilter<5, KB200_CONSTANT>(planes, 1, H, W, grid, lazy); break;
+      case 3: if (H > 1 && W > 1) test_sepfilter<3, KB200_REFLECT>(1, planes, H, W, grid, lazy); break;
+      case 4: if (H > 2) test_pyrdown<KB200_REFLECT>(planes, 2 * ((H + 1) / 2) + 2, W, grid, lazy); break;
+      case 5: test_pyrdown<KB200_CONSTANT>(planes, 2 * ((H + 1) / 2), W, grid, lazy); break;
+      case 6: if (H > 2) test_gradient<5, 3, false>(planes, H, W, grid, lazy); break;
+      case 7: if (H > 1) test_gradient<3, 2, true>(planes, H, W, grid, lazy); break;
+      case 8: if (H > 5 && W > 5) test_ssim<11>(planes, H, W, grid, lazy); break;
+      default: if (H > 3 && W > 3) test_ssim<7>(planes, H, W, grid, lazy); break;
+    }
+  }
+}
+
+int main(int argc, char** argv) {
+  if (argc == 3 && std::string(argv[1]) == "--fuzz") {
+    fuzz(atoi(argv[2]));
+    printf("%s: %d failing comparisons in the fuzz run\n", failures ? "FAILED" : "PASSED", failures);
+    return failures ? 1 : 0;
+  }
   for (int lazy = 0; lazy < 2; ++lazy) {
     // grids that do not divide the number of strips / bands: segments that start in the middle of a band
     test_sepfilter<11, KB200_REFLECT>(2, 3, 70, 132, 5, lazy);
