@@ -28,6 +28,7 @@ alignas(128) unsigned char gradt_smem[256 * 1024];
 alignas(128) unsigned char ssimv_smem[256 * 1024];
 alignas(128) float ssim_smem[64 * 1024];
 alignas(128) unsigned char remap_smem[256 * 1024];
+alignas(128) unsigned char tma_smem[256 * 1024];
 alignas(128) unsigned char bwd_smem[256 * 1024];
 alignas(128) unsigned char bwd2_smem[256 * 1024];
 void set_error(const char*, ...) {}
@@ -186,6 +187,24 @@ static void test_pyrdown(int planes, int H, int W, unsigned grid, bool lazy) {
   }
 }
 
+template <int K, int BORDER>
+static void test_filter2d(int planes, int H, int W, unsigned grid, bool lazy) {
+  emu::lazy_tma = lazy;
+  std::vector<float> xs, os;
+  float* x = aligned(xs, (size_t)planes * H * W);
+  for (size_t i = 0; i < (size_t)planes * H * W; ++i) x[i] = randv(1)[0];
+  auto taps = randv(K * K, -1.f, 1.f);
+  std::vector<float> want((size_t)planes * H * W);
+  ref_filter2d(x, taps.data(), 1, want.data(), planes, H, W, K, BORDER);
+  float* o = aligned(os, want.size());
+  const CUtensorMap map = emu::make_map(x, W, H, planes, SEPT_BW, SEPT_TH + K - 1, 1);
+  F2dTiledParams p{taps.data(), o, 1, H, W, 1, planes};
+  emu::launch(grid, dim3(256), [&] { filter2d_tiled_kernel<K, BORDER, false>(map, p); });
+  compare("filter2d_tiled_kernel (verified on hw) K=" + std::to_string(K) + " border=" + std::to_string(BORDER) + " " + std::to_string(planes) + "x" +
+              std::to_string(H) + "x" + std::to_string(W) + " grid=" + std::to_string(grid) + (lazy ? " lazy" : " eager"),
+          o, want.data(), want.size());
+}
+
 template <int K, int NOUT, bool MAG>
 static void test_gradient(int planes, int H, int W, unsigned grid, bool lazy) {
   emu::lazy_tma = lazy;
@@ -316,6 +335,50 @@ static void test_undistort(int B, int H, int W, bool lazy) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ tiled warp forward (the headline kernel)
+template <bool PROJ, int PAD, int TW, int TH, int BW, int BH>
+static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool lazy, bool tame) {
+  emu::lazy_tma = lazy;
+  emu::set_smem(tma_smem, sizeof(tma_smem));
+  constexpr int C = 3;
+  constexpr bool ALIGN = true;
+  const size_t ns = (size_t)B * C * H * W, no = (size_t)B * C * h * w;
+  std::vector<float> ss, o1s, o2s;
+  float* src = aligned(ss, ns);
+  for (size_t i = 0; i < ns; ++i) src[i] = randv(1)[0];
+  std::vector<float> m((size_t)B * 9), bx(w), by(h);
+  for (int i = 0; i < w; ++i) bx[i] = ((float)i / (float)std::max(w - 1, 1) - 0.5f) * 2.f;
+  for (int i = 0; i < h; ++i) by[i] = ((float)i / (float)std::max(h - 1, 1) - 0.5f) * 2.f;
+  for (int b = 0; b < B; ++b) {
+    const float t = tame ? 0.004f * (b - 1) : (b == 2 ? 0.436f : 0.02f * b);
+    const float M[9] = {cosf(t) * (1.f + (tame ? 0.004f : 0.03f) * b), -sinf(t), (tame ? 0.01f : 0.05f) * b - (!tame && b == 1 ? 0.7f : 0.f), sinf(t),
+                        cosf(t) * (tame ? 0.995f : 0.97f), tame ? -0.008f : -0.03f, PROJ ? (tame ? 0.004f : 0.02f) : 0.f, PROJ ? (tame ? -0.003f : -0.015f) : 0.f, 1.f};
+    memcpy(&m[(size_t)b * 9], M, sizeof(M));
+  }
+  float* o1 = aligned(o1s, no);
+  float* o2 = aligned(o2s, no);
+  TmaWarpParams p{};
+  p.src = src; p.m = m.data(); p.bx = bx.data(); p.by = by.data(); p.fill = nullptr;
+  p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.align = 1; p.debug_copy_only = 0; p.only_class = 0;
+  // oracle: the exact per-pixel path of the same header (the generic kernel's arithmetic, verified against torch on hardware)
+  p.out = o2;
+  for (int b = 0; b < B; ++b)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        const float* mm = &m[(size_t)b * 9];
+        careful_pixel<C, KB200_BILINEAR, PAD, PROJ, ALIGN>(p, b, y, x, mm[0] * bx[x], mm[3] * bx[x], PROJ ? mm[6] * bx[x] : 0.f, mm[1] * by[y], mm[4] * by[y],
+                                                          PROJ ? mm[7] * by[y] : 0.f, mm[2], mm[5], mm[8]);
+      }
+  p.out = o1;
+  const CUtensorMap map = emu::make_map(src, W, H, B * C, BW, BH, C);
+  emu::launch(grid, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, KB200_BILINEAR, PAD, PROJ, ALIGN, TW, TH, BW, BH, 2>(map, p); });
+  compare(std::string("warp_fwd_tma (headline, verified on hw) vs its exact path ") + (PROJ ? "projective " : "affine ") + "pad=" + std::to_string(PAD) + " tile " +
+              std::to_string(TW) + "x" + std::to_string(TH) + " " + std::to_string(B) + "x3x" + std::to_string(H) + "x" + std::to_string(W) + " -> " + std::to_string(h) +
+              "x" + std::to_string(w) + " grid=" + std::to_string(grid) + (lazy ? " lazy" : " eager") + (tame ? " tame" : " wild"),
+          o1, o2, no);
+}
+
 // ------------------------------------------------------------------------------------------ tiled warp backward
 template <bool PROJ>
 static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool lazy, bool tame = false) {
@@ -438,7 +501,15 @@ static void fuzz(int rounds) {
   for (int r = 0; r < rounds; ++r) {
     const int H = pick(1, 110), W = 4 * pick(1, 70), planes = pick(1, 4), lazy = pick(0, 1);
     const unsigned grid = (unsigned)pick(1, 9);
-    switch (pick(0, 9)) {
+    switch (pick(0, 17)) {
+      case 10: if (H > 1 && W > 1) test_filter2d<3, KB200_REFLECT>(planes, H, W, grid, lazy); break;
+      case 11: if (H > 3 && W > 3) test_filter2d<7, KB200_REPLICATE>(planes, H, W, grid, lazy); break;
+      case 12: test_filter2d<7, KB200_CONSTANT>(planes, H, W, grid, lazy); break;
+      case 13: if (H > 1) test_undistort(pick(1, 2), H, W, lazy); break;
+      case 14: if (H > 1 && W > 4) test_backward<true>(3, H, W, std::max(2, H - pick(0, 3)), std::max(8, W - 4 * pick(0, 2)), grid, lazy, pick(0, 1)); break;
+      case 16: if (H > 1) test_forward<true, KB200_ZEROS, 64, 32, 72, 40>(3, H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 1)); break;
+      case 17: if (H > 1) test_forward<false, KB200_BORDER, 32, 32, 56, 56>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
+      case 15: if (H > 1 && W > 4) test_backward<false>(3, std::max(2, H - 1), W, H, W, grid, lazy, true); break;
       case 0: if (H > 5 && W > 5) test_sepfilter<11, KB200_REFLECT>(1, planes, H, W, grid, lazy); break;
       case 1: if (H > 8 && W > 8) test_sepfilter<17, KB200_REPLICATE>(1, planes, H, W, grid, lazy); break;
       case 2: test_sepfilter<5, KB200_CONSTANT>(planes, 1, H, W, grid, lazy); break;
@@ -482,6 +553,10 @@ int main(int argc, char** argv) {
     test_ssim<9>(1, 6, 8, 1, lazy);
     test_undistort(2, 70, 132, lazy);
     test_undistort(1, 33, 64, lazy);
+    test_forward<true, KB200_ZEROS, 64, 32, 72, 40>(3, 96, 200, 96, 200, 3, lazy, true);
+    test_forward<true, KB200_ZEROS, 64, 32, 72, 40>(3, 70, 132, 50, 100, 2, lazy, false);
+    test_forward<false, KB200_BORDER, 64, 32, 72, 40>(3, 64, 128, 70, 132, 4, lazy, true);
+    test_forward<true, KB200_ZEROS, 32, 32, 56, 56>(3, 70, 132, 70, 132, 3, lazy, false);
     test_backward<true>(3, 70, 132, 70, 132, 2, lazy);
     test_backward<false>(3, 64, 128, 50, 96, 3, lazy);
     test_backward<true>(3, 40, 72, 66, 132, 4, lazy);

@@ -70,3 +70,4 @@ inline void bulk_wait0() { emu_bulk_wait(false); }
 inline float rcp_approx(float den) { return 1.0f / den; }  // any approximation within the refinement's basin gives the same quotients
 inline void prefetch_3d(const CUtensorMap*, int, int, int) {}
 inline void prefetch_map(const CUtensorMap*) {}
+inline void prefetch_l1(size_t) {}
