@@ -337,7 +337,7 @@ static void test_undistort(int B, int H, int W, bool lazy) {
 
 
 // ------------------------------------------------------------------------------------------ tiled warp forward (the headline kernel)
-template <bool PROJ, int PAD, int TW, int TH, int BW, int BH>
+template <bool PROJ, int PAD, int TW, int TH, int BW, int BH, int INTERP = KB200_BILINEAR>
 static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool lazy, bool tame) {
   emu::lazy_tma = lazy;
   emu::set_smem(tma_smem, sizeof(tma_smem));
@@ -359,7 +359,8 @@ static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool 
   float* o1 = aligned(o1s, no);
   float* o2 = aligned(o2s, no);
   TmaWarpParams p{};
-  p.src = src; p.m = m.data(); p.bx = bx.data(); p.by = by.data(); p.fill = nullptr;
+  const float fillc[3] = {0.25f, 0.5f, 0.75f};
+  p.src = src; p.m = m.data(); p.bx = bx.data(); p.by = by.data(); p.fill = fillc;
   p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.align = 1; p.debug_copy_only = 0; p.only_class = 0;
   // oracle: the exact per-pixel path of the same header (the generic kernel's arithmetic, verified against torch on hardware)
   p.out = o2;
@@ -367,13 +368,13 @@ static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool 
     for (int y = 0; y < h; ++y)
       for (int x = 0; x < w; ++x) {
         const float* mm = &m[(size_t)b * 9];
-        careful_pixel<C, KB200_BILINEAR, PAD, PROJ, ALIGN>(p, b, y, x, mm[0] * bx[x], mm[3] * bx[x], PROJ ? mm[6] * bx[x] : 0.f, mm[1] * by[y], mm[4] * by[y],
+        careful_pixel<C, INTERP, PAD, PROJ, ALIGN>(p, b, y, x, mm[0] * bx[x], mm[3] * bx[x], PROJ ? mm[6] * bx[x] : 0.f, mm[1] * by[y], mm[4] * by[y],
                                                           PROJ ? mm[7] * by[y] : 0.f, mm[2], mm[5], mm[8]);
       }
   p.out = o1;
   const CUtensorMap map = emu::make_map(src, W, H, B * C, BW, BH, C);
-  emu::launch(grid, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, KB200_BILINEAR, PAD, PROJ, ALIGN, TW, TH, BW, BH, 2>(map, p); });
-  compare(std::string("warp_fwd_tma (headline, verified on hw) vs its exact path ") + (PROJ ? "projective " : "affine ") + "pad=" + std::to_string(PAD) + " tile " +
+  emu::launch(grid, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, INTERP, PAD, PROJ, ALIGN, TW, TH, BW, BH, 2>(map, p); });
+  compare(std::string("warp_fwd_tma (headline, verified on hw) vs its exact path ") + (PROJ ? "projective " : "affine ") + "interp=" + std::to_string(INTERP) + " pad=" + std::to_string(PAD) + " tile " +
               std::to_string(TW) + "x" + std::to_string(TH) + " " + std::to_string(B) + "x3x" + std::to_string(H) + "x" + std::to_string(W) + " -> " + std::to_string(h) +
               "x" + std::to_string(w) + " grid=" + std::to_string(grid) + (lazy ? " lazy" : " eager") + (tame ? " tame" : " wild"),
           o1, o2, no);
@@ -557,6 +558,11 @@ int main(int argc, char** argv) {
     test_forward<true, KB200_ZEROS, 64, 32, 72, 40>(3, 70, 132, 50, 100, 2, lazy, false);
     test_forward<false, KB200_BORDER, 64, 32, 72, 40>(3, 64, 128, 70, 132, 4, lazy, true);
     test_forward<true, KB200_ZEROS, 32, 32, 56, 56>(3, 70, 132, 70, 132, 3, lazy, false);
+    test_forward<true, KB200_REFLECTION, 64, 32, 72, 40>(3, 70, 132, 70, 132, 3, lazy, false);
+    test_forward<true, KB200_FILL, 64, 32, 72, 40>(3, 70, 132, 64, 120, 2, lazy, true);
+    test_forward<true, KB200_ZEROS, 64, 32, 72, 40, KB200_NEAREST>(3, 70, 132, 70, 132, 3, lazy, true);
+    test_forward<true, KB200_BORDER, 64, 32, 72, 40, KB200_BICUBIC>(3, 70, 132, 70, 132, 2, lazy, true);
+    test_forward<false, KB200_REFLECTION, 64, 32, 72, 40, KB200_BICUBIC>(3, 64, 128, 70, 132, 3, lazy, false);
     test_backward<true>(3, 70, 132, 70, 132, 2, lazy);
     test_backward<false>(3, 64, 128, 50, 96, 3, lazy);
     test_backward<true>(3, 40, 72, 66, 132, 4, lazy);
