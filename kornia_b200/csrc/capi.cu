@@ -250,6 +250,9 @@ int kb200_remap_forward(const void* src, const void* map_x, const void* map_y, v
   KB_CHECK_ARG(map_x && map_y && out, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == KB200_F32) {
+    rc = remap_warp_forward((const float*)src, (const float*)map_x, (const float*)map_y, nullptr, (float*)out, B, C, H, W, h, w, Bmap, normalized,
+                            interp, pad, align_corners, st);  // opt-in (KB200_REMAP_V2=1), declines otherwise
+    if (rc != KB200_EUNSUPPORTED) return rc;
     rc = remap_tiled_forward((const float*)src, (const float*)map_x, (const float*)map_y, (float*)out, B, C, H, W, h, w, Bmap, normalized,
                              interp, pad, align_corners, st);
     if (rc != KB200_EUNSUPPORTED) return rc;
@@ -263,7 +266,11 @@ int kb200_undistort_forward(const void* src, const void* lens, void* out, int B,
   KB_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "non-positive shape");
   KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
   int rc = KB200_EUNSUPPORTED;
-  if (dtype == KB200_F32) rc = undistort_tiled_forward((const float*)src, (const float*)lens, (float*)out, B, C, H, W, (cudaStream_t)stream);
+  if (dtype == KB200_F32) {
+    rc = remap_warp_forward((const float*)src, nullptr, nullptr, (const float*)lens, (float*)out, B, C, H, W, H, W, B, 0, KB200_BILINEAR, KB200_ZEROS, 1,
+                            (cudaStream_t)stream);  // opt-in (KB200_REMAP_V2=1), declines otherwise
+    if (rc == KB200_EUNSUPPORTED) rc = undistort_tiled_forward((const float*)src, (const float*)lens, (float*)out, B, C, H, W, (cudaStream_t)stream);
+  }
   if (rc == KB200_EUNSUPPORTED) set_error("the fused undistort kernel covers fp32 images of 1 or 3 channels with a width divisible by 4");
   return rc;
 }

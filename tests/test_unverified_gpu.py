@@ -283,3 +283,43 @@ def test_fused_undistort_golden_and_fallbacks(monkeypatch):
     cam = torch.tensor([[[50.0, 0, 32], [0, 50.0, 16], [0, 0, 1]]], device=DEV)
     KC.undistort_image(img, cam, torch.tensor([[0.1, 0.0, 0.0, 0.0]], device=DEV)).sum().backward()   # grad: composition
     assert img.grad is not None
+
+
+# ------------------------------------------------------------------------------------------ warp-pipelined remap
+@pytest.mark.parametrize("pad", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("ac", [True, False, None])
+@pytest.mark.parametrize("C", [3, 1])
+def test_remap_v2_bit_identical(monkeypatch, pad, ac, C):
+    """remap_warp_kernel (KB200_REMAP_V2=1) == remap_tiled_kernel: smooth, noisy, out-of-view and NaN maps; shared and
+    per-sample maps; output size different from the input size."""
+    g = torch.Generator().manual_seed(7)
+    B, H, W, h, w = 3, 120, 256, 100, 232
+    img = torch.rand(B, C, H, W, generator=g).to(DEV)
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    base_x, base_y = xx * (W - 1) / (w - 1), yy * (H - 1) / (h - 1)
+    r2 = ((base_x - W / 2) / W) ** 2 + ((base_y - H / 2) / H) ** 2
+    smooth = torch.stack([base_x + 9 * r2 * (base_x - W / 2) / W * 8, base_x * 0.5 - 20, base_x + 3 * torch.randn(h, w, generator=g)])
+    smooth_y = torch.stack([base_y + 9 * r2 * (base_y - H / 2) / H * 8, base_y * 1.5 + 30, base_y + 3 * torch.randn(h, w, generator=g)])
+    smooth_y[1, 5, 7] = float("nan")
+    for mx, my in ((smooth, smooth_y), (smooth[:1], smooth_y[:1])):
+        mx, my = mx.to(DEV), my.to(DEV)
+        monkeypatch.delenv("KB200_REMAP_V2", raising=False)
+        want = K.remap(img, mx, my, padding_mode=pad, align_corners=ac)
+        monkeypatch.setenv("KB200_REMAP_V2", "1")
+        got = K.remap(img, mx, my, padding_mode=pad, align_corners=ac)
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0)), float((got - want).abs().nan_to_num().max())
+
+
+def test_remap_v2_full_size_and_fused_undistort(monkeypatch):
+    monkeypatch.setenv("KB200_REMAP_V2", "1")
+    img = torch.rand(2, 3, 1080, 1920, device=DEV)
+    cam = torch.tensor([[1500.0, 0.0, 960.0], [0.0, 1500.0, 540.0], [0.0, 0.0, 1.0]], device=DEV).expand(2, 3, 3).contiguous()
+    dist = torch.tensor([[-0.2, 0.05, 0.001, -0.002, 0.01]], device=DEV).expand(2, 5).contiguous()
+    KC = K.geometry.calibration
+    a = KC.undistort_image(img, cam, dist)                 # maps (torch) + remap v2
+    monkeypatch.setenv("KB200_FUSED_UNDISTORT", "1")
+    b = KC.undistort_image(img, cam, dist)                 # lens model inside remap v2
+    monkeypatch.delenv("KB200_REMAP_V2")
+    monkeypatch.delenv("KB200_FUSED_UNDISTORT")
+    c = KC.undistort_image(img, cam, dist)                 # maps (torch) + the verified tiled remap
+    assert torch.equal(a, c) and torch.equal(b, c)

@@ -75,4 +75,11 @@ with torch.no_grad():
     pair("pyrdown", "KB200_FUSED_PYRDOWN", lambda: K.geometry.transform.pyrdown(x), 5)
     cam = torch.tensor([[1500.0, 0.0, 960.0], [0.0, 1500.0, 540.0], [0.0, 0.0, 1.0]], device=dev).expand(B, 3, 3).contiguous()
     dist = torch.tensor([[-0.2, 0.05, 0.001, -0.002, 0.01]], device=dev).expand(B, 5).contiguous()
+    yy, xx = torch.meshgrid(torch.arange(H, device=dev, dtype=torch.float32), torch.arange(W, device=dev, dtype=torch.float32), indexing="ij")
+    r2 = ((xx - W / 2) / W) ** 2 + ((yy - H / 2) / H) ** 2
+    mx, my = (xx + 40 * r2 * (xx - W / 2) / W)[None].contiguous(), (yy + 40 * r2 * (yy - H / 2) / H)[None].contiguous()
+    pair("remap (shared radial map)", "KB200_REMAP_V2", lambda: K.remap(x, mx, my, align_corners=True), 8 + 8 / (3 * B))
+    mxb, myb = mx.expand(B, H, W).contiguous(), my.expand(B, H, W).contiguous()
+    pair("remap (per-sample maps)", "KB200_REMAP_V2", lambda: K.remap(x, mxb, myb, align_corners=True), 8 + 8 / 3)
+    pair("undistort_image (maps + remap v2)", "KB200_REMAP_V2", lambda: K.geometry.calibration.undistort_image(x, cam, dist), 8)
     pair("undistort_image (5 coefficients)", "KB200_FUSED_UNDISTORT", lambda: K.geometry.calibration.undistort_image(x, cam, dist), 8)

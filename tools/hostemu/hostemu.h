@@ -274,6 +274,10 @@ void emu_spin() {
   emu::yield();
 }
 long long& emu_bar_tx(uint64_t* bar) { return emu::bar_tx[bar]; }
+long long& emu_lds_count() {
+  static long long n = 0;
+  return n;
+}
 uint32_t emu_smem_addr(const void* p) {
   const char* c = static_cast<const char*>(p);
   if (!emu::smem_base || c < emu::smem_base || c >= emu::smem_base + emu::smem_size) emu::fail("smem_u32 of a pointer outside the CTA's shared array");

@@ -14,7 +14,7 @@
 #include "../../kornia_b200/csrc/gradient_tiled.cuh"
 #include "../../kornia_b200/csrc/sepfilter_vwalk.cuh"
 #include "../../kornia_b200/csrc/ssim_vwalk.cuh"
-#include "../../kornia_b200/csrc/remap_tiled.cuh"
+#include "../../kornia_b200/csrc/remap_warp.cuh"
 #include "../../kornia_b200/csrc/warp_bwd_tma2.cuh"
 
 #include <random>
@@ -29,6 +29,7 @@ alignas(128) unsigned char ssimv_smem[256 * 1024];
 alignas(128) float ssim_smem[64 * 1024];
 alignas(128) unsigned char remap_smem[256 * 1024];
 alignas(128) unsigned char tma_smem[256 * 1024];
+alignas(128) unsigned char remapw_smem[256 * 1024];
 alignas(128) unsigned char bwd_smem[256 * 1024];
 alignas(128) unsigned char bwd2_smem[256 * 1024];
 void set_error(const char*, ...) {}
@@ -288,7 +289,7 @@ static float ref_remap_pixel(const float* plane, int H, int W, float mx, float m
   return a;
 }
 
-static void test_undistort(int B, int H, int W, bool lazy) {
+static void test_undistort(int B, int H, int W, bool lazy, bool strong = false) {
   emu::lazy_tma = lazy;
   emu::set_smem(remap_smem, sizeof(remap_smem));
   constexpr int C = 3;
@@ -298,7 +299,8 @@ static void test_undistort(int B, int H, int W, bool lazy) {
   for (size_t i = 0; i < n; ++i) src[i] = randv(1)[0];
   std::vector<float> lens((size_t)B * 16);
   for (int b = 0; b < B; ++b) {
-    const float L[16] = {0.8f * W + 3 * b, 0.75f * W, 0.5f * W - 3.f, 0.5f * H + 2.f, -0.21f, 0.07f, 0.002f, -0.003f, 0.01f, 0.04f, -0.02f, 0.004f, 0.003f, -0.001f, 0.002f, 0.0015f};
+    // strong: a fish-eye-like model whose maps leave the 8-row windows (and partly the image): the exact per-pixel path
+    const float L[16] = {(strong ? 0.35f : 0.8f) * W + 3 * b, (strong ? 0.3f : 0.75f) * W, 0.5f * W - 3.f, 0.5f * H + 2.f, strong ? -0.45f : -0.21f, 0.07f, 0.002f, -0.003f, 0.01f, 0.04f, -0.02f, 0.004f, 0.003f, -0.001f, 0.002f, 0.0015f};
     memcpy(&lens[(size_t)b * 16], L, sizeof(L));
   }
   // the maps the host composition would hand to remap: lens_distort on the exact integer grid (the same device function)
@@ -320,7 +322,7 @@ static void test_undistort(int B, int H, int W, bool lazy) {
   }
   const CUtensorMap map = emu::make_map(src, W, H, B * C, 72, 40, C);
   const dim3 grid(ceil_div(W, 64), ceil_div(H, 32), B);
-  const std::string tag = std::to_string(B) + "x3x" + std::to_string(H) + "x" + std::to_string(W) + (lazy ? " lazy" : " eager");
+  const std::string tag = std::to_string(B) + "x3x" + std::to_string(H) + "x" + std::to_string(W) + (lazy ? " lazy" : " eager") + (strong ? " strong" : "");
   float* o1 = aligned(o1s, n);
   {
     RemapTiledParams p{src, mx, my, o1, B, H, W, H, W, B, 0, nullptr};
@@ -332,6 +334,22 @@ static void test_undistort(int B, int H, int W, bool lazy) {
     RemapTiledParams p{src, nullptr, nullptr, o2, B, H, W, H, W, B, 0, lens.data()};
     emu::launch3(grid, dim3(256), [&] { remap_tiled_kernel<3, KB200_ZEROS, true, true>(map, p); });
     compare("remap_tiled_kernel<LENS> (fused undistort) vs maps + remap " + tag, o2, o1, n);
+  }
+  {  // the warp-pipelined persistent kernels, on grids that cut the schedule into segments
+    emu::set_smem(remapw_smem, sizeof(remapw_smem));
+    const CUtensorMap wmap = emu::make_map(src, W, H, B * C, 72, REMAPW_SH, C);
+    const unsigned g2 = 1 + (unsigned)((H + W) % 5);
+    for (size_t i = 0; i < n; ++i) o2[i] = -55.f;
+    RemapTiledParams p{src, mx, my, o2, B, H, W, H, W, B, 0, nullptr};
+    const long long lds0 = tma::emu_lds_count();
+    emu::launch(g2, dim3(256), [&] { remap_warp_kernel<3, KB200_ZEROS, true, false>(wmap, p); });
+    printf("     remap_warp_kernel: %.0f %% of the pixels served from the per-warp windows\n", 100.0 * (double)(tma::emu_lds_count() - lds0) / 12.0 / (double)npix);
+    compare("remap_warp_kernel (per-warp pipelines) vs remap_tiled_kernel   " + tag + " grid=" + std::to_string(g2), o2, o1, n);
+    for (size_t i = 0; i < n; ++i) o2[i] = -55.f;
+    RemapTiledParams pl{src, nullptr, nullptr, o2, B, H, W, H, W, B, 0, lens.data()};
+    emu::launch(g2, dim3(256), [&] { remap_warp_kernel<3, KB200_ZEROS, true, true>(wmap, pl); });
+    compare("remap_warp_kernel<LENS> (fused undistort) vs remap_tiled_kernel " + tag + " grid=" + std::to_string(g2), o2, o1, n);
+    emu::set_smem(remap_smem, sizeof(remap_smem));
   }
 }
 
@@ -554,6 +572,7 @@ int main(int argc, char** argv) {
     test_ssim<9>(1, 6, 8, 1, lazy);
     test_undistort(2, 70, 132, lazy);
     test_undistort(1, 33, 64, lazy);
+    test_undistort(2, 97, 200, lazy, true);
     test_forward<true, KB200_ZEROS, 64, 32, 72, 40>(3, 96, 200, 96, 200, 3, lazy, true);
     test_forward<true, KB200_ZEROS, 64, 32, 72, 40>(3, 70, 132, 50, 100, 2, lazy, false);
     test_forward<false, KB200_BORDER, 64, 32, 72, 40>(3, 64, 128, 70, 132, 4, lazy, true);

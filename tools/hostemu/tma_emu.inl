@@ -52,7 +52,11 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 inline void load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   emu_tma_issue(dst, reinterpret_cast<const EmuMap*>(map), bar, c0, c1, c2);
 }
-inline float lds(uint32_t a) { return *emu_smem_ptr(a); }
+long long& emu_lds_count();
+inline float lds(uint32_t a) {
+  ++emu_lds_count();
+  return *emu_smem_ptr(a);
+}
 inline float lds_ro(uint32_t a) { return *emu_smem_ptr(a); }
 inline void sts(uint32_t a, float v) { *emu_smem_ptr(a) = v; }
 inline bool elect_one() {  // elect.sync: a warp collective that picks one lane
