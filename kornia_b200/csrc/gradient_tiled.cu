@@ -28,6 +28,8 @@ int spatial_gradient_tiled_forward(const float* x, const double* taps, float* ou
                                    double eps, cudaStream_t st) {
   const char* on = getenv("KB200_TILED_GRADIENT");  // off by default: not yet run on hardware
   if (!(on && on[0] == '1')) return KB200_EUNSUPPORTED;
+  const char* off = getenv("KB200_DISABLE_TILED_FILTER");
+  if (off && off[0] == '1') return KB200_EUNSUPPORTED;
   if (!x || !out || !taps || (k != 3 && k != 5) || nout < 2 || nout > GRAD_MAX_OUT) return KB200_EUNSUPPORTED;
   if (magnitude && (nout != 2 || k != 3)) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return KB200_EUNSUPPORTED;

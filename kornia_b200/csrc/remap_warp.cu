@@ -27,6 +27,8 @@ int remap_warp_forward(const float* src, const float* map_x, const float* map_y,
                        int w, int Bmap, int normalized, int interp, int pad, int align, cudaStream_t st) {
   const char* on = getenv("KB200_REMAP_V2");  // off by default: not yet run on hardware
   if (!(on && on[0] == '1')) return KB200_EUNSUPPORTED;
+  const char* off = getenv("KB200_DISABLE_TMA");  // tests use it to reach the generic kernel
+  if (off && off[0] == '1') return KB200_EUNSUPPORTED;
   if (interp != KB200_BILINEAR || (C != 1 && C != 3) || pad == KB200_FILL) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || (long long)B * ceil_div(h, 32) > 0x7fffffffll) return KB200_EUNSUPPORTED;
   if (lens && (pad != KB200_ZEROS || !align || h != H || w != W)) return KB200_EUNSUPPORTED;

@@ -27,6 +27,8 @@ int sepfilter_vwalk_forward(const float* x, const float* kx, const float* ky, fl
                             int Bky, int kh, int border, int same, cudaStream_t st, const float* lerp_w) {
   const char* on = getenv("KB200_SEP_VWALK");  // off by default: not yet run on hardware
   if (!(on && on[0] == '1')) return KB200_EUNSUPPORTED;
+  const char* off = getenv("KB200_DISABLE_TILED_FILTER");  // tests use it to reach the generic kernel
+  if (off && off[0] == '1') return KB200_EUNSUPPORTED;
   if (!same || kw != kh || (kw & 1) == 0 || kw < 3 || kw > 17 || border == KB200_CIRCULAR) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 7) != 0) return KB200_EUNSUPPORTED;
   const int halo = (kw - 1) / 2;

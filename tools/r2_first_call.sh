@@ -22,6 +22,10 @@ KB200_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_unverified_gpu.py
 echo "rc=$?" >> "$OUT/pytest_unverified.log"
 tail -15 "$OUT/pytest_unverified.log" | tee -a "$OUT/steps.log"
 
+step "2b the whole GPU suite THROUGH the opt-in kernels (every golden / fp64 / gradcheck / full-size test of round 1)"
+KB200_OPTIN=all timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > "$OUT/pytest_gpu_optin.log" 2>&1; echo "rc=$?" >> "$OUT/pytest_gpu_optin.log"
+tail -5 "$OUT/pytest_gpu_optin.log" | tee -a "$OUT/steps.log"
+
 step "3 bench lines (headline, blur, fwd+bwd) and the CPU arm"
 for wl in warp blur warp_bwd; do
   timeout 400 python bench.py --workload $wl > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"; echo "$wl rc=$?" | tee -a "$OUT/steps.log"
