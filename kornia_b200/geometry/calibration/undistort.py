@@ -1,8 +1,10 @@
 """Drop-in ``undistort_image`` (reference: kornia/geometry/calibration/undistort.py:138-198):
 every output pixel is pushed through the lens model (``distort_points``) to find where the distorted image holds
 it, and the image is resampled there by ``remap`` -- the tiled TMA kernel of csrc/remap_tiled.cuh (bilinear,
-zeros, align_corners=True).  The maps are (B,H,W) torch tensors as in the reference; fusing their evaluation into
-the sampling kernel (8 B/pixel less traffic and ~40 fewer launches) is the listed next step."""
+zeros, align_corners=True).  By default the maps are (B,H,W) torch tensors as in the reference.  The one-kernel form
+(kb200_undistort_forward: the lens model evaluated per pixel in registers, no maps, ~45 fewer elementwise passes) is
+written and passes on the host emulator but has not run on hardware yet: opt-in with KB200_FUSED_UNDISTORT=1 (DESIGN.md
+section 9)."""
 from __future__ import annotations
 
 import os

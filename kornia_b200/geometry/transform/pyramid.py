@@ -5,7 +5,9 @@ The blur is the 5x5 binomial stencil through :func:`kornia_b200.filters.filter2d
 kernel of csrc/filter2d_tiled.cuh (border folded into the tile load, no ``F.pad`` copy).  The 2x
 resampling step is ``torch.nn.functional.interpolate``, the third-party call the reference itself makes
 at pyramid.py:450-455,496-498 (the reference's own ``TODO: use kornia.geometry.resize``): 5 B/element of
-traffic next to the blur's 8, left to ATen.  ``ScalePyramid`` (the SIFT octave builder) is a feature-
+traffic next to the blur's 8, left to ATen by default.  At an exact factor of two the resampling is a 2x2 average and
+runs in the blur kernel's epilogue (kb200_pyrdown_forward): written, passes on the host emulator, not yet run on
+hardware, opt-in with KB200_FUSED_PYRDOWN=1.  ``ScalePyramid`` (the SIFT octave builder) is a feature-
 detection caller and stays out of scope."""
 from __future__ import annotations
 
