@@ -3,6 +3,14 @@
 
 namespace kb200 {
 
+// Experiment knob for the persistent opt-in kernels: resident CTAs per SM the grid is sized for (default: the kernel's
+// launch bounds).  KB200_GRID_PER_SM=1|2|3 -- a smaller grid means fewer, longer-running CTAs (less L2 / TMA contention).
+static inline long long grid_per_sm(long long dflt) {
+  const char* e = getenv("KB200_GRID_PER_SM");
+  const int v = e ? atoi(e) : 0;
+  return (v >= 1 && v <= dflt) ? v : dflt;
+}
+
 template <int NC, int PAD, bool ALIGN, bool LENS>
 static int launch_remap_warp(const CUtensorMap& map, const RemapTiledParams& p, cudaStream_t st) {
   auto kern = remap_warp_kernel<NC, PAD, ALIGN, LENS>;
@@ -12,7 +20,7 @@ static int launch_remap_warp(const CUtensorMap& map, const RemapTiledParams& p, 
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   const long long nstrips = (long long)p.B * ceil_div(p.h, 32);
-  const long long cap = (LENS ? 2ll : 3ll) * sm_count();  // = the kernel's launch bounds
+  const long long cap = grid_per_sm(LENS ? 2 : 3) * sm_count();  // default = the kernel's launch bounds
   const int grid = (int)(nstrips < cap ? nstrips : cap);
   kern<<<grid, 256, smem, st>>>(map, p);
   cudaError_t e = cudaGetLastError();

@@ -3,6 +3,14 @@
 
 namespace kb200 {
 
+// Experiment knob for the persistent opt-in kernels: resident CTAs per SM the grid is sized for (default: the kernel's
+// launch bounds).  KB200_GRID_PER_SM=1|2|3 -- a smaller grid means fewer, longer-running CTAs (less L2 / TMA contention).
+static inline long long grid_per_sm(long long dflt) {
+  const char* e = getenv("KB200_GRID_PER_SM");
+  const int v = e ? atoi(e) : 0;
+  return (v >= 1 && v <= dflt) ? v : dflt;
+}
+
 template <int K, int BORDER, bool LERP = false>
 static int launch_sep_vwalk(const CUtensorMap& map_main, const CUtensorMap& map_pro, const SepTiledParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)(2 * SEPT_TH * SEPT_BW + (SEPT_TH + K - 1) * SEPT_TW) * 4 + 2 * sizeof(uint64_t);
@@ -12,7 +20,7 @@ static int launch_sep_vwalk(const CUtensorMap& map_main, const CUtensorMap& map_
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   const long long nbands = (long long)p.planes * ceil_div(p.W, SEPT_TW);
-  const long long cap = 3ll * sm_count();
+  const long long cap = grid_per_sm(3) * sm_count();
   const int grid = (int)(nbands < cap ? nbands : cap);
   kern<<<grid, 256, smem, st>>>(map_main, map_pro, p);
   cudaError_t e = cudaGetLastError();

@@ -3,6 +3,14 @@
 
 namespace kb200 {
 
+// Experiment knob for the persistent opt-in kernels: resident CTAs per SM the grid is sized for (default: the kernel's
+// launch bounds).  KB200_GRID_PER_SM=1|2|3 -- a smaller grid means fewer, longer-running CTAs (less L2 / TMA contention).
+static inline long long grid_per_sm(long long dflt) {
+  const char* e = getenv("KB200_GRID_PER_SM");
+  const int v = e ? atoi(e) : 0;
+  return (v >= 1 && v <= dflt) ? v : dflt;
+}
+
 template <int K>
 static int launch_ssimv(const CUtensorMap maps[4], const SsimVParams& p, cudaStream_t st) {
   auto kern = ssim_vwalk_kernel<K>;
@@ -10,7 +18,7 @@ static int launch_ssimv(const CUtensorMap maps[4], const SsimVParams& p, cudaStr
   if (first_use_on_device(configured))
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssimv_smem_bytes<K>()));
   const long long nbands = (long long)p.planes * ceil_div(p.W, SSIMV_TW);
-  const long long cap = 2ll * sm_count();
+  const long long cap = grid_per_sm(2) * sm_count();
   const int grid = (int)(nbands < cap ? nbands : cap);
   kern<<<grid, 256, ssimv_smem_bytes<K>(), st>>>(maps[0], maps[1], maps[2], maps[3], p);
   cudaError_t e = cudaGetLastError();

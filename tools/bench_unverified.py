@@ -60,6 +60,22 @@ def pair(name, switch, fn, bytes_per_elem):
     del ref, got
 
 
+def sweep(name, switch, fn):
+    """The opt-in persistent kernels at 1 / 2 / 3 resident CTAs per SM (KB200_GRID_PER_SM; values above a kernel's launch bounds
+    are ignored by the library)."""
+    os.environ[switch] = "1"
+    out = []
+    for g in ("1", "2", "3"):
+        os.environ["KB200_GRID_PER_SM"] = g
+        try:
+            out.append(f"{g}: {timed(fn):7.3f} ms")
+        except Exception as exc:
+            out.append(f"{g}: FAILED {exc}")
+    os.environ.pop("KB200_GRID_PER_SM", None)
+    os.environ.pop(switch, None)
+    print(f"{name:34s} {switch}=1, CTAs per SM the grid is sized for -> " + " | ".join(out))
+
+
 with torch.no_grad():
     print(f"B={B} x 3 x {H} x {W} fp32, measured HBM peak {peak:.0f} GB/s; bytes = algorithmic bytes of the fused op")
     pair("gaussian_blur2d k=11 (cfg3)", "KB200_SEP_VWALK", lambda: K.gaussian_blur2d(x, (11, 11), (2.0, 2.0)), 8)
@@ -83,3 +99,6 @@ with torch.no_grad():
     pair("remap (per-sample maps)", "KB200_REMAP_V2", lambda: K.remap(x, mxb, myb, align_corners=True), 8 + 8 / 3)
     pair("undistort_image (maps + remap v2)", "KB200_REMAP_V2", lambda: K.geometry.calibration.undistort_image(x, cam, dist), 8)
     pair("undistort_image (5 coefficients)", "KB200_FUSED_UNDISTORT", lambda: K.geometry.calibration.undistort_image(x, cam, dist), 8)
+    sweep("gaussian_blur2d k=11 (cfg3)", "KB200_SEP_VWALK", lambda: K.gaussian_blur2d(x, (11, 11), (2.0, 2.0)))
+    sweep("ssim window 11", "KB200_SSIM_VWALK", lambda: K.metrics.ssim(x, y, 11))
+    sweep("remap (per-sample maps)", "KB200_REMAP_V2", lambda: K.remap(x, mxb, myb, align_corners=True))
