@@ -11,7 +11,6 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.nn.functional as F
 
 from .. import _prelude as P
 from ... import _lib
