@@ -19,7 +19,7 @@ __version__ = "0.1.0"
 # KB200_OPTIN=all turns every one of them on for this process, so that the WHOLE GPU test suite can be run through them
 # (`KB200_OPTIN=all python -m pytest tests -m gpu`): the C library reads the switches with getenv at call time.
 OPTIN_SWITCHES = ("KB200_SEP_VWALK", "KB200_SSIM_VWALK", "KB200_TILED_GRADIENT", "KB200_BWD_V2", "KB200_REMAP_V2", "KB200_FUSED_UNDISTORT",
-                  "KB200_FUSED_PYRDOWN")
+                  "KB200_FUSED_PYRDOWN", "KB200_FAST_FILTER_BWD")
 if __import__("os").environ.get("KB200_OPTIN") == "all":
     for _name in OPTIN_SWITCHES:
         __import__("os").environ.setdefault(_name, "1")

@@ -3,6 +3,7 @@ torch's; every FLOP on an image is executed by kornia_b200/csrc kernels."""
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -287,6 +288,9 @@ class SepFilterFunction(torch.autograd.Function):
         x, kx, ky = ctx.saved_tensors
         border, same = ctx.cfg
         need = ctx.needs_input_grad
+        if need[0] and not (need[1] or need[2]) and same and os.environ.get("KB200_FAST_FILTER_BWD") == "1":
+            # opt-in: input-only gradient without rebuilding the forward through the generic kernels
+            return _sep_input_gradient(gout.contiguous(), kx, ky, border), None, None, None, None
         with torch.enable_grad():
             xl = x.detach().requires_grad_(need[0])
             kxl = kx.detach().requires_grad_(need[1])
@@ -297,6 +301,44 @@ class SepFilterFunction(torch.autograd.Function):
             grads = list(torch.autograd.grad(out, wrt, gout.contiguous())) if wrt else []
         res = [grads.pop(0) if n else None for n in need[:3]]
         return res[0], res[1], res[2], None, None
+
+
+def _filter2d_backward_input(gout: torch.Tensor, kernel: torch.Tensor, border: int) -> torch.Tensor:
+    """The C call Filter2dFunction.backward makes for d/dinput ('same'), without the autograd graph around it."""
+    B, C, H, W = gout.shape
+    Bk, kh, kw = kernel.shape
+    gx = torch.empty_like(gout)
+    if gx.numel() > 0:
+        with torch.cuda.device(gout.device):
+            _lib.call("kb200_filter2d_backward_input", _ptr(gout), _ptr(kernel), _ptr(gx), B, C, H, W, Bk, kh, kw, border, 1, _dtype_code(gout),
+                      _stream(gout))
+        _bump()
+    return gx
+
+
+def _sep_input_gradient(gout: torch.Tensor, kx: torch.Tensor, ky: torch.Tensor, border: int) -> torch.Tensor:
+    """d/dinput of the 'same' separable filter.  Exact form: the two adjoint passes of the composition (the very calls
+    autograd makes, minus the two forward passes it rebuilds first).  When the one-pass tiled kernel covers the shape, the
+    image-sized work runs through it instead (adjoint = correlation with the flipped taps under a 'constant' border) and
+    only the border bands take the exact form (filters/_adjoint.py)."""
+    from .filters._adjoint import separable_adjoint
+
+    def exact(g, kx_, ky_):
+        g_mid = _filter2d_backward_input(g, ky_[:, :, None].contiguous(), border)
+        return _filter2d_backward_input(g_mid, kx_[:, None, :].contiguous(), border)
+
+    def forward_constant(g, kx_, ky_):
+        out = torch.empty_like(g)
+        B, C, H, W = g.shape
+        with torch.cuda.device(g.device):
+            _lib.call("kb200_sepfilter_forward", _ptr(g), _ptr(kx_.contiguous()), _ptr(ky_.contiguous()), _ptr(out), B, C, H, W, kx_.shape[0],
+                      kx_.shape[1], ky_.shape[0], ky_.shape[1], _lib.CONSTANT, 1, _dtype_code(g), _stream(g))
+        _bump()
+        return out
+
+    kw, kh = kx.shape[-1], ky.shape[-1]
+    fast = gout.dtype == torch.float32 and kw == kh and kw % 2 == 1 and 3 <= kw <= 17 and border != _lib.CIRCULAR and gout.shape[-1] % 4 == 0
+    return separable_adjoint(gout, kx, ky, border, forward_constant, exact) if fast else exact(gout, kx, ky)
 
 
 class SpatialGradientFunction(torch.autograd.Function):

@@ -323,3 +323,49 @@ def test_remap_v2_full_size_and_fused_undistort(monkeypatch):
     monkeypatch.delenv("KB200_FUSED_UNDISTORT")
     c = KC.undistort_image(img, cam, dist)                 # maps (torch) + the verified tiled remap
     assert torch.equal(a, c) and torch.equal(b, c)
+
+
+# ------------------------------------------------------------------------------------------ fast filter backward
+@pytest.mark.parametrize("border", ["reflect", "replicate", "constant"])
+@pytest.mark.parametrize("ksize", [3, 11])
+@pytest.mark.parametrize("shape", [(2, 3, 70, 132), (1, 1, 20, 36), (1, 3, 360, 640)])
+def test_fast_filter_backward_matches_composition(monkeypatch, border, ksize, shape):
+    """KB200_FAST_FILTER_BWD=1: d/dinput of gaussian_blur2d through the forward kernel with flipped taps + exact border bands,
+    against the autograd composition (four generic passes) -- different summation order, fp32 rounding apart."""
+    from helpers import rel_l2
+
+    x = torch.rand(*shape, device=DEV)
+    cot = torch.rand(*shape, device=DEV) - 0.5
+
+    def grad():
+        xx = x.clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(K.gaussian_blur2d(xx, (ksize, ksize), (1.7, 1.7), border), [xx], cot)
+        return g
+
+    monkeypatch.delenv("KB200_FAST_FILTER_BWD", raising=False)
+    want = grad()
+    monkeypatch.setenv("KB200_FAST_FILTER_BWD", "1")
+    got = grad()
+    assert rel_l2(got, want) < 2e-6, rel_l2(got, want)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-6)
+
+
+def test_fast_filter_backward_ssim_loss_and_goldens(monkeypatch):
+    from helpers import family_grads, rel_l2
+
+    monkeypatch.setenv("KB200_FAST_FILTER_BWD", "1")
+    SS, FIL = golden("ssim"), golden("filter")
+    for name in SS.names("ssim_grad") + SS.names("ssim_loss_grad"):
+        op, kw, ins, outs = SS.case(name)
+        impl = K.losses if op.startswith("ssim_loss") else K.metrics
+        got = family_grads(impl, op, kw, ins, outs, device=DEV)
+        for key, want in outs.items():
+            if key != "cot":
+                assert rel_l2(got[key].cpu(), want) < 1e-4, (name, key)
+    from helpers import run_case
+    for name in FIL.names("gaussian_blur2d_grad") + FIL.names("filter2d_separable_grad"):
+        op, kw, ins, outs = FIL.case(name)
+        got = run_case(K, op, kw, ins, device=DEV)
+        for key, want in outs.items():
+            if key != "cot":
+                assert rel_l2(got[key].cpu(), want) < 1e-4, (name, key)

@@ -99,6 +99,24 @@ with torch.no_grad():
     pair("remap (per-sample maps)", "KB200_REMAP_V2", lambda: K.remap(x, mxb, myb, align_corners=True), 8 + 8 / 3)
     pair("undistort_image (maps + remap v2)", "KB200_REMAP_V2", lambda: K.geometry.calibration.undistort_image(x, cam, dist), 8)
     pair("undistort_image (5 coefficients)", "KB200_FUSED_UNDISTORT", lambda: K.geometry.calibration.undistort_image(x, cam, dist), 8)
+
+def blur_backward():
+    xx = x.detach().requires_grad_(True)
+    (g,) = torch.autograd.grad(K.gaussian_blur2d(xx, (11, 11), (2.0, 2.0)), [xx], y)
+    return g
+
+
+os.environ.pop("KB200_FAST_FILTER_BWD", None)
+ref = blur_backward()
+t0 = timed(blur_backward, 3)
+os.environ["KB200_FAST_FILTER_BWD"] = "1"
+got = blur_backward()
+t1 = timed(blur_backward, 3)
+os.environ.pop("KB200_FAST_FILTER_BWD", None)
+err = float((got - ref).norm() / ref.norm())
+print(f"{'gaussian_blur2d k=11 fwd + d/dinput':34s} default {t0:7.3f} ms | KB200_FAST_FILTER_BWD=1 {t1:7.3f} ms | x{t0 / t1:4.2f} | rel-L2 vs default {err:.1e}")
+del ref, got
+with torch.no_grad():
     sweep("gaussian_blur2d k=11 (cfg3)", "KB200_SEP_VWALK", lambda: K.gaussian_blur2d(x, (11, 11), (2.0, 2.0)))
     sweep("ssim window 11", "KB200_SSIM_VWALK", lambda: K.metrics.ssim(x, y, 11))
     sweep("remap (per-sample maps)", "KB200_REMAP_V2", lambda: K.remap(x, mxb, myb, align_corners=True))
