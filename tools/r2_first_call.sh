@@ -35,6 +35,7 @@ timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_
 step "4 timings of the unverified variants against the defaults"
 timeout 400 python tools/bench_unverified.py > "$OUT/bench_unverified.txt" 2>&1; echo "rc=$?" | tee -a "$OUT/steps.log"
 timeout 300 python tools/bench_family.py > "$OUT/family_B64.txt" 2>&1
+timeout 300 python tools/bench_vs_torch.py > "$OUT/vs_torch.txt" 2>&1   # the BASELINE configs against torch eager on the same GPU
 # the two BASELINE workloads with their opt-in kernels: full bench lines (roofline leg included)
 KB200_SEP_VWALK=1 timeout 400 python bench.py --workload blur --no-cpu-baseline > "$OUT/bench_blur_vwalk.json" 2> "$OUT/bench_blur_vwalk.err"
 KB200_BWD_V2=1 timeout 400 python bench.py --workload warp_bwd --no-cpu-baseline > "$OUT/bench_warp_bwd_v2.json" 2> "$OUT/bench_warp_bwd_v2.err"
