@@ -114,6 +114,18 @@ int kb200_remap_backward(const void* gout, const void* src, const void* map_x, c
  * layer only calls it when KB200_FUSED_UNDISTORT=1. */
 int kb200_undistort_forward(const void* src, const void* lens, void* out, int B, int C, int H, int W, int dtype, void* stream);
 
+/* Warp straight from a decoder's interleaved uint8 output: image_to_tensor
+ * (kornia/image/utils.py:27, HWC -> CHW) + _to_float32 (kornia/io/io.py:108-111, image.float() / 255.0) + warp_perspective /
+ * warp_affine (imgwarp.py:69,177) in ONE kernel.  src (B,H,W,C) uint8; m / bx / by / fill fp32 as for kb200_warp_forward;
+ * out (B,C,h,w) fp32.  normalize: 0 keeps float(byte); 1 multiplies by the fp32 reciprocal of 255, which is how torch's
+ * CUDA backend evaluates `image.float() / 255.0` (so the result is bit-identical to the reference's three steps on this
+ * device); 2 divides, as torch's CPU backend does (one ulp apart for 126 of the 256 byte values).  Forward only (a uint8 image has no gradient).
+ * Status: written after the round-1 GPU budget was spent -- compiled for sm_100a, executed on the host emulator, not yet
+ * run on hardware. */
+int kb200_warp_u8hwc_forward(const void* src_u8, const void* m, const void* bx, const void* by, const void* fill, void* out,
+                             int B, int C, int H, int W, int h, int w, int Bm, int projective, int interp, int pad,
+                             int align_corners, int normalize, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * filter2d core (filters/filter.py:136-150: F.pad + view + depthwise F.conv2d + view).
  *   x      (B,C,H,W)

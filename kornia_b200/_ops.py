@@ -125,6 +125,32 @@ class WarpFunction(torch.autograd.Function):
         return (gsrc, gm) + (None,) * 9
 
 
+def warp_u8hwc(image: torch.Tensor, m: torch.Tensor, bx: torch.Tensor, by: torch.Tensor, fill: Optional[torch.Tensor], h: int, w: int,
+               projective: bool, interp: int, pad: int, align: bool, normalize: int) -> torch.Tensor:
+    """Warp of an interleaved uint8 batch (B,H,W,C) into planar fp32 (B,C,h,w) in one kernel (kb200_warp_u8hwc_forward):
+    the bytes are converted tap by tap inside the sampler (``normalize``: 0 raw, 1 times 1/255 as torch's CUDA backend
+    does, 2 divided by 255).  ``m`` is the (B|1,3,3) fp32 sampling matrix of the warp prelude.  Forward only."""
+    _require_cuda(image, "image")
+    if image.dtype != torch.uint8:
+        raise RuntimeError(f"kornia_b200: expected a uint8 image, got {image.dtype}")
+    if m.device != image.device:
+        raise RuntimeError(f"Expected all tensors to be on the same device, but the transformation matrix is on {m.device} and the image on {image.device}")
+    img = image.contiguous()
+    f32 = dict(device=image.device, dtype=torch.float32)
+    m_c, bx, by = m.to(**f32).contiguous(), bx.to(**f32).contiguous(), by.to(**f32).contiguous()
+    fill_c = None if fill is None else fill.to(**f32).contiguous()
+    B, H, W, C = img.shape
+    out = torch.empty((B, C, h, w), **f32)
+    if out.numel() > 0 and img.numel() > 0:
+        with torch.cuda.device(image.device), _Timed("warp_u8hwc_forward", image):
+            _lib.call("kb200_warp_u8hwc_forward", _ptr(img), _ptr(m_c), _ptr(bx), _ptr(by), _ptr(fill_c), _ptr(out), B, C, H, W, h, w,
+                      m_c.shape[0], int(projective), interp, pad, int(align), int(normalize), _stream(image))
+        _bump()
+    else:
+        out.zero_()
+    return out
+
+
 class RemapFunction(torch.autograd.Function):
     """out = sample(image, (map_x, map_y)); differentiable w.r.t. the image and both maps."""
 

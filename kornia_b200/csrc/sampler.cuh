@@ -232,6 +232,37 @@ struct PixelSampler {
     }
   }
 
+  // The same blend with the taps supplied by ``fetch(offset)`` (offset = row * W + column of the tap, in pixels): lets a
+  // kernel whose source is not a planar T image (warp_u8.cuh: interleaved uint8) share the tap order and rounding of
+  // sample() without touching it.
+  template <typename F>
+  __device__ __forceinline__ T sample_with(F fetch) const {
+    using R = RN<T>;
+    if (INTERP == KB200_BILINEAR) {
+      T acc = T(0);
+      if (ok[0]) acc = R::fma(fetch(o), w[0], acc);
+      if (ok[1]) acc = R::fma(fetch(o + 1), w[1], acc);
+      if (ok[2]) acc = R::fma(fetch(o + W), w[2], acc);
+      if (ok[3]) acc = R::fma(fetch(o + W + 1), w[3], acc);
+      return acc;
+    } else if (INTERP == KB200_NEAREST) {
+      return ok[0] ? fetch(o) : T(0);
+    } else {
+      T acc = T(0);
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        T r = T(0);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const T v = (yok[i] && xok[j]) ? fetch(yo[i] + xo[j]) : T(0);
+          r = R::fma(v, cx[j], r);
+        }
+        acc = R::fma(r, cy[i], acc);
+      }
+      return acc;
+    }
+  }
+
   // value written for a channel: sample (+ (1 - coverage) * fill for PAD == KB200_FILL)
   __device__ __forceinline__ T finish(T v, T fill) const {
     using R = RN<T>;

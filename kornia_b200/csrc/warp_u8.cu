@@ -1,0 +1,75 @@
+// kornia_b200 -- host side of the uint8 ingest warp (warp_u8.cuh) and its C entry point.
+#include "warp_u8.cuh"
+
+namespace kb200 {
+
+constexpr int U8_MAX_Z = 65535;
+
+template <int INTERP, int PAD, int KIND>
+static int launch_u8(const WarpU8Params& p, cudaStream_t st) {
+  const dim3 block(GEN_BX, GEN_BY);
+  for (int b0 = 0; b0 < p.B; b0 += U8_MAX_Z) {
+    WarpU8Params q = p;
+    q.B = min(U8_MAX_Z, p.B - b0);
+    q.src = p.src + (size_t)b0 * p.H * p.W * p.C;
+    q.out = p.out + (size_t)b0 * p.C * p.h * p.w;
+    if (p.Bm != 1) q.m = p.m + (size_t)b0 * 9;
+    const dim3 grid(ceil_div(p.w, GEN_BX), ceil_div(p.h, GEN_BY), q.B);
+    if (p.C == 3)
+      warp_fwd_u8hwc<INTERP, PAD, KIND, 3><<<grid, block, 0, st>>>(q);
+    else if (p.C == 1)
+      warp_fwd_u8hwc<INTERP, PAD, KIND, 1><<<grid, block, 0, st>>>(q);
+    else
+      warp_fwd_u8hwc<INTERP, PAD, KIND, 0><<<grid, block, 0, st>>>(q);
+  }
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("warp_u8hwc_forward: kernel launch failed: %s", cudaGetErrorString(e));
+    return KB200_ECUDA;
+  }
+  return KB200_OK;
+}
+
+template <int INTERP, int KIND>
+static int by_pad(const WarpU8Params& p, int pad, cudaStream_t st) {
+  switch (pad) {
+    case KB200_ZEROS: return launch_u8<INTERP, KB200_ZEROS, KIND>(p, st);
+    case KB200_BORDER: return launch_u8<INTERP, KB200_BORDER, KIND>(p, st);
+    case KB200_REFLECTION: return launch_u8<INTERP, KB200_REFLECTION, KIND>(p, st);
+    case KB200_FILL: return launch_u8<INTERP, KB200_FILL, KIND>(p, st);
+  }
+  set_error("bad pad %d", pad);
+  return KB200_EINVAL;
+}
+
+template <int KIND>
+static int by_interp(const WarpU8Params& p, int interp, int pad, cudaStream_t st) {
+  switch (interp) {
+    case KB200_BILINEAR: return by_pad<KB200_BILINEAR, KIND>(p, pad, st);
+    case KB200_NEAREST: return by_pad<KB200_NEAREST, KIND>(p, pad, st);
+    case KB200_BICUBIC: return by_pad<KB200_BICUBIC, KIND>(p, pad, st);
+  }
+  set_error("bad interp %d", interp);
+  return KB200_EINVAL;
+}
+
+}  // namespace kb200
+
+using namespace kb200;
+
+int kb200_warp_u8hwc_forward(const void* src, const void* m, const void* bx, const void* by, const void* fill, void* out, int B, int C,
+                             int H, int W, int h, int w, int Bm, int projective, int interp, int pad, int align_corners,
+                             int normalize, void* stream) {
+  KB_CHECK_ARG(src && m && bx && by && out, "null pointer argument");
+  KB_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && h > 0 && w > 0, "non-positive shape B=%d C=%d H=%d W=%d h=%d w=%d", B, C, H, W, h, w);
+  KB_CHECK_ARG((long long)H * W < (1ll << 31) && (long long)h * w < (1ll << 31), "plane too large for 32-bit in-plane offsets");
+  KB_CHECK_ARG(Bm == B || Bm == 1, "matrix batch %d must be %d or 1", Bm, B);
+  KB_CHECK_ARG(pad != KB200_FILL || fill, "pad=fill needs a fill vector");
+  KB_CHECK_ARG(normalize >= 0 && normalize <= 2, "normalize must be 0 (raw), 1 (times 1/255) or 2 (divided by 255), got %d", normalize);
+  WarpU8Params p{};
+  p.src = (const unsigned char*)src; p.m = (const float*)m; p.bx = (const float*)bx; p.by = (const float*)by;
+  p.fill = (const float*)fill; p.out = (float*)out;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = Bm; p.align = align_corners; p.normalize = normalize;
+  cudaStream_t st = (cudaStream_t)stream;
+  return projective ? by_interp<KIND_PROJ>(p, interp, pad, st) : by_interp<KIND_AFFINE>(p, interp, pad, st);
+}

@@ -633,3 +633,27 @@ def undistort_image(image, K, dist):
     moved = distort_points(grid, K, dist)
     out = remap(image.reshape(n, C, H, W), moved[..., 0].reshape(n, H, W), moved[..., 1].reshape(n, H, W), align_corners=True)
     return out.view_as(image)
+
+
+# --------------------------------------------------------------------------------------
+# uint8 ingest
+# --------------------------------------------------------------------------------------
+def image_to_float(image, normalize=True):
+    """kornia/image/utils.py:60-73 (image_to_tensor: (H,W,C) -> (1,C,H,W) with keepdim=False, (B,H,W,C) -> (B,C,H,W) by
+    permute) followed by kornia/io/io.py:108-111 (_to_float32: image.float() / 255.0)."""
+    x = image.unsqueeze(0) if image.dim() == 3 else image
+    x = x.permute(0, 3, 1, 2)
+    return x.float() / 255.0 if normalize else x.float()
+
+
+def warp_perspective_from_uint8(image, M, dsize, mode="bilinear", padding_mode="zeros", align_corners=True, fill_value=None,
+                                normalize=True):
+    """The three steps a caller of the reference writes for decoder output: image_to_tensor, _to_float32, warp_perspective
+    (imgwarp.py:69)."""
+    return warp_perspective(image_to_float(image, normalize), M, dsize, mode, padding_mode, align_corners, fill_value)
+
+
+def warp_affine_from_uint8(image, M, dsize, mode="bilinear", padding_mode="zeros", align_corners=True, fill_value=None,
+                           normalize=True):
+    """image_to_tensor, _to_float32, warp_affine (imgwarp.py:177)."""
+    return warp_affine(image_to_float(image, normalize), M, dsize, mode, padding_mode, align_corners, fill_value)

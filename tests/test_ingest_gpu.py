@@ -1,0 +1,88 @@
+"""GPU parity of the uint8 ingest warps (csrc/warp_u8.cuh) through the C ABI.  The kernel was written
+after the round-1 GPU budget was spent: it has run on the host emulator only, nothing else in the library calls it, and
+these tests are skipped unless KB200_RUN_UNVERIFIED=1 (tools/r2_first_call.sh runs them):
+
+    KB200_RUN_UNVERIFIED=1 python -m pytest tests/test_ingest_gpu.py -m gpu -q
+"""
+import os
+
+import pytest
+import torch
+
+import kornia_b200 as K
+from conftest import golden
+from helpers import run_family_case
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("KB200_RUN_UNVERIFIED") != "1", reason="unverified device code: set KB200_RUN_UNVERIFIED=1")]
+DEV = "cuda"
+ING = golden("ingest")
+KT = K.geometry.transform
+
+
+@pytest.mark.parametrize("name", ING.names())
+def test_ingest_matches_reference(name):
+    """Golden vectors of image_to_tensor + _to_float32 + warp_* recorded from the reference on CPU: 1e-4 rel (north_star)."""
+    op, kw, ins, outs = ING.case(name)
+    before = K._ops.launch_count
+    got = run_family_case(KT, op, kw, ins, device=DEV)
+    assert K._ops.launch_count == before + 1 + (1 if ins["M"].shape[0] >= 2 else 0)  # the warp (+ the one-launch prelude)
+    assert got.is_cuda and got.dtype == torch.float32 and got.shape == outs["out"].shape and got.is_contiguous()
+    if kw["mode"] == "nearest":
+        # a rounding tie of the index may fall on the other side between host and device
+        bad = (got.cpu() - outs["out"]).abs() > (1e-5 + 1e-4 * outs["out"].abs())
+        assert bad.float().mean().item() <= 0.02
+    else:
+        torch.testing.assert_close(got.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ING.names())
+def test_ingest_is_bit_identical_to_the_three_steps_on_device(name):
+    """Same device, same sampler arithmetic: permute + .float() / 255 + the fp32 warp of this library == one kernel."""
+    op, kw, ins, outs = ING.case(name)
+    got = run_family_case(KT, op, kw, ins, device=DEV)
+    img = ins["image"].to(DEV)
+    img = img.unsqueeze(0) if img.dim() == 3 else img
+    x = img.permute(0, 3, 1, 2).float()
+    x = x / 255.0 if kw.get("normalize", True) else x
+    fn = KT.warp_affine if op.startswith("warp_affine") else KT.warp_perspective
+    args = {k: (tuple(v) if isinstance(v, list) else v) for k, v in kw.items() if k != "normalize"}
+    if "fill_value" in ins:
+        args["fill_value"] = ins["fill_value"].to(DEV)
+    want = fn(x.contiguous(), ins["M"].to(DEV), **args)
+    assert torch.equal(got, want), float((got - want).abs().max())
+
+
+def test_ingest_full_size_properties():
+    """1080p: the identity homography returns byte / 255 exactly (bilinear weights 1, 0, 0, 0); a pure integer translation
+    moves the image and fills with zeros; frames with every byte value."""
+    B, H, W = 4, 1080, 1920
+    frames = torch.randint(0, 256, (B, H, W, 3), device=DEV, dtype=torch.uint8)
+    frames[0, :16, :16, 0] = torch.arange(256, device=DEV, dtype=torch.uint8).reshape(16, 16)
+    eye = torch.eye(3, device=DEV).expand(B, 3, 3).contiguous()
+    want = frames.permute(0, 3, 1, 2).float() / 255.0
+    for mode in ("bilinear", "nearest"):
+        got = KT.warp_perspective_from_uint8(frames, eye, (H, W), mode=mode)
+        assert torch.equal(got, want)
+    exact = KT.warp_perspective_from_uint8(frames[:1], eye[:1], (H, W), normalize="exact")  # torch's CPU form: a true division
+    assert torch.equal(exact.cpu(), frames[:1].cpu().permute(0, 3, 1, 2).float() / 255.0)
+    raw = KT.warp_perspective_from_uint8(frames, eye, (H, W), normalize=False)
+    assert torch.equal(raw, frames.permute(0, 3, 1, 2).float())
+    shift = eye.clone()
+    shift[:, 0, 2], shift[:, 1, 2] = 7.0, -3.0
+    got = KT.warp_perspective_from_uint8(frames, shift, (H, W), mode="nearest")
+    assert torch.equal(got[..., :-3, 7:], want[..., 3:, :-7]) and float(got[..., -3:, :].abs().max()) == 0.0 and float(got[..., :7].abs().max()) == 0.0
+    one = KT.warp_affine_from_uint8(frames[0], eye[:1, :2], (H, W))
+    assert one.shape == (1, 3, H, W) and torch.equal(one[0], want[0])
+
+
+def test_ingest_headline_homographies_match_the_fp32_path():
+    """The bench's jittered-corner homographies at 1080p: equal to the TMA-tiled fp32 warp of the converted frames."""
+    import bench
+
+    B, H, W = 4, 1080, 1920
+    frames = torch.randint(0, 256, (B, H, W, 3), device=DEV, dtype=torch.uint8)
+    M = bench.make_homographies(B, 5).to(DEV)
+    got = KT.warp_perspective_from_uint8(frames, M, (H, W))
+    want = KT.warp_perspective((frames.permute(0, 3, 1, 2).float() / 255.0).contiguous(), M, (H, W))
+    assert torch.equal(got, want), float((got - want).abs().max())

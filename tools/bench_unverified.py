@@ -100,6 +100,33 @@ with torch.no_grad():
     pair("undistort_image (maps + remap v2)", "KB200_REMAP_V2", lambda: K.geometry.calibration.undistort_image(x, cam, dist), 8)
     pair("undistort_image (5 coefficients)", "KB200_FUSED_UNDISTORT", lambda: K.geometry.calibration.undistort_image(x, cam, dist), 8)
 
+def ingest():
+    """uint8 ingest warp against the three steps it replaces, on the headline homographies."""
+    import bench
+
+    KT = K.geometry.transform
+    frames = torch.randint(0, 256, (B, H, W, 3), device=dev, dtype=torch.uint8)
+    M = bench.make_homographies(B, 1000).to(dev)
+    steps = lambda: KT.warp_perspective((frames.permute(0, 3, 1, 2).float() / 255.0), M, (H, W))  # noqa: E731
+    fused = lambda: KT.warp_perspective_from_uint8(frames, M, (H, W))  # noqa: E731
+    try:
+        ref = steps()
+        t0 = timed(steps)
+        got = fused()
+        same = torch.equal(got, ref)
+        t1 = timed(fused)
+    except Exception as exc:
+        print(f"{'warp_perspective_from_uint8':34s} FAILED: {exc}")
+        return
+    gb = B * H * W * 15 / 1e9  # 3 bytes read + 12 written per pixel
+    print(f"{'warp_perspective_from_uint8':34s} permute+float+/255+warp {t0:7.3f} ms | one kernel {t1:7.3f} ms ({gb / t1 / peak * 1e3 * 100:5.1f} % HBM "
+          f"of 15 B/pixel) | x{t0 / t1:4.2f} | {'bit-identical' if same else 'MISMATCH'}")
+
+
+with torch.no_grad():
+    ingest()
+
+
 def blur_backward():
     xx = x.detach().requires_grad_(True)
     (g,) = torch.autograd.grad(K.gaussian_blur2d(xx, (11, 11), (2.0, 2.0)), [xx], y)

@@ -16,6 +16,7 @@
 #include "../../kornia_b200/csrc/ssim_vwalk.cuh"
 #include "../../kornia_b200/csrc/remap_warp.cuh"
 #include "../../kornia_b200/csrc/warp_bwd_tma2.cuh"
+#include "../../kornia_b200/csrc/warp_u8.cuh"
 
 #include <random>
 #include <string>
@@ -514,6 +515,71 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
 
 // Random shapes, grids and completion modes (run_emu --fuzz N): shakes out the edge cases the fixed list does not name
 // -- images smaller than a tile, one-row last tiles, bands narrower than the halo, more CTAs than strips.
+// ------------------------------------------------------------------------------------------ uint8 ingest warp
+// warp_fwd_u8hwc on interleaved bytes against the hardware-verified generic kernel on the planar fp32 image the
+// reference would have built first (io.py:111 as torch evaluates it: a real division on CPU, times 1.0f / 255.0f on CUDA): bit for bit.
+template <int INTERP, int PAD, int KIND>
+static void test_u8(int B, int C, int H, int W, int h, int w, bool align, int normalize, bool shared_m) {
+  const size_t npix = (size_t)B * H * W, no = (size_t)B * C * h * w;
+  std::vector<unsigned char> bytes(npix * C);
+  for (auto& v : bytes) v = (unsigned char)(rng() & 255);
+  std::vector<float> planar(npix * C), o1(no, -1.f), o2(no, -2.f), m((size_t)B * 9), bx(w), by(h);
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < C; ++c)
+      for (int i = 0; i < H * W; ++i) {
+        const float f = (float)bytes[((size_t)b * H * W + i) * C + c];
+        planar[((size_t)b * C + c) * H * W + i] = normalize == 2 ? f / 255.0f : normalize == 1 ? f * (1.0f / 255.0f) : f;
+      }
+  for (int i = 0; i < w; ++i) bx[i] = ((float)i / (float)std::max(w - 1, 1) - 0.5f) * 2.f;
+  for (int i = 0; i < h; ++i) by[i] = ((float)i / (float)std::max(h - 1, 1) - 0.5f) * 2.f;
+  for (int b = 0; b < B; ++b) {
+    const float t = 0.3f * b - 0.2f;
+    const float M[9] = {cosf(t) * (1.f + 0.1f * b), -sinf(t), 0.2f * b - 0.3f, sinf(t), cosf(t) * 0.9f, 0.15f,
+                        KIND == KIND_PROJ ? 0.05f : 0.f, KIND == KIND_PROJ ? -0.04f : 0.f, 1.f};
+    memcpy(&m[(size_t)b * 9], M, sizeof(M));
+  }
+  const float fillc[4] = {0.25f, 0.5f, 0.75f, 1.f};
+  const int Bm = shared_m ? 1 : B;
+  WarpParams<float> g{};
+  g.src = planar.data(); g.m = m.data(); g.bx = bx.data(); g.by = by.data(); g.fill = fillc; g.out = o2.data();
+  g.B = B; g.C = C; g.H = H; g.W = W; g.h = h; g.w = w; g.Bm = Bm; g.align = align; g.normalized = 0;
+  WarpU8Params u{};
+  u.src = bytes.data(); u.m = m.data(); u.bx = bx.data(); u.by = by.data(); u.fill = fillc; u.out = o1.data();
+  u.B = B; u.C = C; u.H = H; u.W = W; u.h = h; u.w = w; u.Bm = Bm; u.align = align; u.normalize = normalize;
+  const dim3 grid(ceil_div(w, GEN_BX), ceil_div(h, GEN_BY), B), block(GEN_BX, GEN_BY);
+  emu::launch3(grid, block, [&] { warp_fwd_generic<float, INTERP, PAD, KIND>(g); });
+  if (C == 3)  // the instantiation the host picks (warp_u8.cu:launch_u8)
+    emu::launch3(grid, block, [&] { warp_fwd_u8hwc<INTERP, PAD, KIND, 3>(u); });
+  else if (C == 1)
+    emu::launch3(grid, block, [&] { warp_fwd_u8hwc<INTERP, PAD, KIND, 1>(u); });
+  else
+    emu::launch3(grid, block, [&] { warp_fwd_u8hwc<INTERP, PAD, KIND, 0>(u); });
+  compare("warp_fwd_u8hwc vs convert + warp_fwd_generic interp=" + std::to_string(INTERP) + " pad=" + std::to_string(PAD) + " kind=" + std::to_string(KIND) + " " +
+              std::to_string(B) + "x" + std::to_string(H) + "x" + std::to_string(W) + "x" + std::to_string(C) + " -> " + std::to_string(h) + "x" + std::to_string(w) +
+              (align ? " align" : "") + (normalize == 2 ? " /255" : normalize == 1 ? " *(1/255)" : " raw") + (shared_m ? " shared matrix" : ""),
+          o1.data(), o2.data(), no);
+}
+
+static void test_u8_all() {
+  int bad = 0;
+  for (int v = 0; v < 256; ++v) bad += unit_from_byte((unsigned char)v) != (float)v / 255.0f;
+  if (bad) {
+    ++failures;
+    printf("FAIL unit_from_byte: %d of 256 bytes differ from float(u) / 255.0f\n", bad);
+  } else {
+    printf("ok   unit_from_byte == float(u) / 255.0f for all 256 bytes\n");
+  }
+  test_u8<KB200_BILINEAR, KB200_ZEROS, KIND_PROJ>(2, 3, 37, 52, 37, 52, true, 1, false);
+  test_u8<KB200_BILINEAR, KB200_BORDER, KIND_PROJ>(2, 3, 37, 52, 29, 61, false, 2, false);
+  test_u8<KB200_BILINEAR, KB200_REFLECTION, KIND_AFFINE>(3, 1, 20, 33, 41, 35, true, 2, true);
+  test_u8<KB200_BILINEAR, KB200_FILL, KIND_PROJ>(2, 3, 37, 52, 37, 52, true, 1, false);
+  test_u8<KB200_NEAREST, KB200_ZEROS, KIND_PROJ>(2, 4, 18, 26, 30, 30, false, 0, false);
+  test_u8<KB200_NEAREST, KB200_FILL, KIND_AFFINE>(1, 3, 18, 26, 18, 26, true, 1, false);
+  test_u8<KB200_BICUBIC, KB200_ZEROS, KIND_PROJ>(2, 3, 37, 52, 37, 52, true, 1, false);
+  test_u8<KB200_BICUBIC, KB200_REFLECTION, KIND_AFFINE>(2, 4, 19, 23, 33, 40, false, 2, false);
+  test_u8<KB200_BICUBIC, KB200_FILL, KIND_PROJ>(1, 3, 16, 16, 20, 24, true, 0, false);
+}
+
 static void fuzz(int rounds) {
   std::mt19937 g(20260923);
   auto pick = [&](int lo, int hi) { return lo + (int)(g() % (unsigned)(hi - lo + 1)); };
@@ -549,6 +615,7 @@ int main(int argc, char** argv) {
     printf("%s: %d failing comparisons in the fuzz run\n", failures ? "FAILED" : "PASSED", failures);
     return failures ? 1 : 0;
   }
+  test_u8_all();
   for (int lazy = 0; lazy < 2; ++lazy) {
     // grids that do not divide the number of strips / bands: segments that start in the middle of a band
     test_sepfilter<11, KB200_REFLECT>(2, 3, 70, 132, 5, lazy);

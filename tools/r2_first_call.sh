@@ -18,7 +18,7 @@ timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider > "$OUT/pyte
 tail -3 "$OUT/pytest_gpu.log" | tee -a "$OUT/steps.log"
 
 step "2 unverified kernels (section 9): parity against the verified paths"
-KB200_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_unverified_gpu.py -m gpu -q -p no:cacheprovider > "$OUT/pytest_unverified.log" 2>&1
+KB200_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_unverified_gpu.py tests/test_ingest_gpu.py -m gpu -q -p no:cacheprovider > "$OUT/pytest_unverified.log" 2>&1
 echo "rc=$?" >> "$OUT/pytest_unverified.log"
 tail -15 "$OUT/pytest_unverified.log" | tee -a "$OUT/steps.log"
 
