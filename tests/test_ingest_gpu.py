@@ -27,7 +27,7 @@ def test_ingest_matches_reference(name):
     before = K._ops.launch_count
     got = run_family_case(KT, op, kw, ins, device=DEV)
     assert K._ops.launch_count == before + 1 + (1 if ins["M"].shape[0] >= 2 else 0)  # the warp (+ the one-launch prelude)
-    assert got.is_cuda and got.dtype == torch.float32 and got.shape == outs["out"].shape and got.is_contiguous()
+    assert got.device.type == torch.device(DEV).type and got.dtype == torch.float32 and got.shape == outs["out"].shape and got.is_contiguous()
     if kw["mode"] == "nearest":
         # a rounding tie of the index may fall on the other side between host and device
         bad = (got.cpu() - outs["out"]).abs() > (1e-5 + 1e-4 * outs["out"].abs())
@@ -54,25 +54,25 @@ def test_ingest_is_bit_identical_to_the_three_steps_on_device(name):
 
 
 def test_ingest_full_size_properties():
-    """1080p: the identity homography returns byte / 255 exactly (bilinear weights 1, 0, 0, 0); a pure integer translation
-    moves the image and fills with zeros; frames with every byte value."""
+    """1080p: the identity homography returns byte / 255 -- exactly under 'nearest'; the normalise / invert / unnormalise
+    chain leaves the coordinates ~1e-4 px off the integers (as in the reference), so 'bilinear' is close, not equal; a
+    pure integer translation moves the image and fills with zeros; frames with every byte value."""
     B, H, W = 4, 1080, 1920
     frames = torch.randint(0, 256, (B, H, W, 3), device=DEV, dtype=torch.uint8)
     frames[0, :16, :16, 0] = torch.arange(256, device=DEV, dtype=torch.uint8).reshape(16, 16)
     eye = torch.eye(3, device=DEV).expand(B, 3, 3).contiguous()
     want = frames.permute(0, 3, 1, 2).float() / 255.0
-    for mode in ("bilinear", "nearest"):
-        got = KT.warp_perspective_from_uint8(frames, eye, (H, W), mode=mode)
-        assert torch.equal(got, want)
-    exact = KT.warp_perspective_from_uint8(frames[:1], eye[:1], (H, W), normalize="exact")  # torch's CPU form: a true division
+    assert torch.equal(KT.warp_perspective_from_uint8(frames, eye, (H, W), mode="nearest"), want)
+    torch.testing.assert_close(KT.warp_perspective_from_uint8(frames, eye, (H, W)), want, rtol=0, atol=1e-3)
+    exact = KT.warp_perspective_from_uint8(frames[:1], eye[:1], (H, W), mode="nearest", normalize="exact")  # torch's CPU form: a true division
     assert torch.equal(exact.cpu(), frames[:1].cpu().permute(0, 3, 1, 2).float() / 255.0)
-    raw = KT.warp_perspective_from_uint8(frames, eye, (H, W), normalize=False)
+    raw = KT.warp_perspective_from_uint8(frames, eye, (H, W), mode="nearest", normalize=False)
     assert torch.equal(raw, frames.permute(0, 3, 1, 2).float())
     shift = eye.clone()
     shift[:, 0, 2], shift[:, 1, 2] = 7.0, -3.0
     got = KT.warp_perspective_from_uint8(frames, shift, (H, W), mode="nearest")
     assert torch.equal(got[..., :-3, 7:], want[..., 3:, :-7]) and float(got[..., -3:, :].abs().max()) == 0.0 and float(got[..., :7].abs().max()) == 0.0
-    one = KT.warp_affine_from_uint8(frames[0], eye[:1, :2], (H, W))
+    one = KT.warp_affine_from_uint8(frames[0], eye[:1, :2], (H, W), mode="nearest")
     assert one.shape == (1, 3, H, W) and torch.equal(one[0], want[0])
 
 
