@@ -1,5 +1,7 @@
 // kornia_b200 -- host side of the uint8 ingest warp (warp_u8.cuh) and its C entry point.
-#include "warp_u8.cuh"
+#include "warp_u8_tiled.cuh"
+
+#include <stdlib.h>
 
 namespace kb200 {
 
@@ -28,6 +30,42 @@ static int launch_u8(const WarpU8Params& p, cudaStream_t st) {
     return KB200_ECUDA;
   }
   return KB200_OK;
+}
+
+// ---------------------------------------------------------------- tiled kernel (warp_u8_tiled.cuh)
+template <int NC, int PAD, bool PROJ, bool ALIGN>
+static int launch_u8_tiled(const WarpU8Params& p, cudaStream_t st) {
+  const dim3 grid(ceil_div(p.w, 64), ceil_div(p.h, 32), p.B);
+  warp_u8_tiled_kernel<NC, PAD, PROJ, ALIGN><<<grid, 256, U8T_SMEM_BYTES(NC), st>>>(p);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("warp_u8hwc_forward (tiled): kernel launch failed: %s", cudaGetErrorString(e));
+    return KB200_ECUDA;
+  }
+  return KB200_OK;
+}
+
+// KB200_EUNSUPPORTED: the request is served by warp_fwd_u8hwc instead.
+static int u8_tiled_forward(const WarpU8Params& p, int projective, int interp, int pad, cudaStream_t st) {
+  const char* simple = getenv("KB200_U8_SIMPLE");
+  if (simple && simple[0] == '1') return KB200_EUNSUPPORTED;
+  if (interp != KB200_BILINEAR || pad == KB200_FILL || (p.C != 1 && p.C != 3)) return KB200_EUNSUPPORTED;
+  // aligned 32-bit loads of whole in-image words: every image row starts on a 4-byte boundary
+  if (((long long)p.W * p.C) % 4 != 0 || (reinterpret_cast<uintptr_t>(p.src) & 3) != 0) return KB200_EUNSUPPORTED;
+  if (p.B > 65535 || ceil_div(p.h, 32) > 65535) return KB200_EUNSUPPORTED;
+#define KB_U8T_CASE(NC_, PAD_)                                                                                             \
+  if (p.C == NC_ && pad == PAD_) {                                                                                         \
+    if (projective) return p.align ? launch_u8_tiled<NC_, PAD_, true, true>(p, st) : launch_u8_tiled<NC_, PAD_, true, false>(p, st);  \
+    return p.align ? launch_u8_tiled<NC_, PAD_, false, true>(p, st) : launch_u8_tiled<NC_, PAD_, false, false>(p, st);     \
+  }
+  KB_U8T_CASE(3, KB200_ZEROS)
+  KB_U8T_CASE(3, KB200_BORDER)
+  KB_U8T_CASE(3, KB200_REFLECTION)
+  KB_U8T_CASE(1, KB200_ZEROS)
+  KB_U8T_CASE(1, KB200_BORDER)
+  KB_U8T_CASE(1, KB200_REFLECTION)
+#undef KB_U8T_CASE
+  return KB200_EUNSUPPORTED;
 }
 
 template <int INTERP, int KIND>
@@ -71,5 +109,9 @@ int kb200_warp_u8hwc_forward(const void* src, const void* m, const void* bx, con
   p.fill = (const float*)fill; p.out = (float*)out;
   p.B = B; p.C = C; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = Bm; p.align = align_corners; p.normalize = normalize;
   cudaStream_t st = (cudaStream_t)stream;
+  KB_CHECK_ARG(interp >= KB200_BILINEAR && interp <= KB200_BICUBIC, "bad interp %d", interp);
+  KB_CHECK_ARG(pad >= KB200_ZEROS && pad <= KB200_FILL, "bad pad %d", pad);
+  const int rc = u8_tiled_forward(p, projective, interp, pad, st);
+  if (rc != KB200_EUNSUPPORTED) return rc;
   return projective ? by_interp<KIND_PROJ>(p, interp, pad, st) : by_interp<KIND_AFFINE>(p, interp, pad, st);
 }

@@ -22,7 +22,7 @@ def test_kernels_on_the_host_emulator():
     assert run.returncode == 0 and "PASSED: 0 failing comparisons" in run.stdout, tail
     for kernel in ("sepfilter_tiled_kernel", "sepfilter_vwalk_kernel", "filter2d_tiled_kernel<5, DOWN2>", "grad_tiled_kernel", "ssim_vwalk_kernel",
                    "remap_tiled_kernel<LENS>", "warp_bwd_tma (verified on hw)", "warp_bwd_tma2", "warp_fwd_tma (headline", "remap_warp_kernel",
-                   "warp_fwd_u8hwc", "unit_from_byte == float(u) / 255.0f for all 256 bytes"):
+                   "warp_fwd_u8hwc", "warp_u8_tiled_kernel vs warp_fwd_u8hwc", "unit_from_byte == float(u) / 255.0f for all 256 bytes"):
         assert kernel in run.stdout, kernel
     assert "FAIL" not in run.stdout, tail
 

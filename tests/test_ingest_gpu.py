@@ -86,3 +86,32 @@ def test_ingest_headline_homographies_match_the_fp32_path():
     got = KT.warp_perspective_from_uint8(frames, M, (H, W))
     want = KT.warp_perspective((frames.permute(0, 3, 1, 2).float() / 255.0).contiguous(), M, (H, W))
     assert torch.equal(got, want), float((got - want).abs().max())
+
+
+@pytest.mark.parametrize("pad", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("channels", [1, 3])
+def test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(monkeypatch, pad, channels):
+    """warp_u8_tiled_kernel (window staged in shared memory, each byte converted once) against warp_fwd_u8hwc (KB200_U8_SIMPLE=1):
+    headline-like homographies, rotations that push tiles to the exact path, a horizon inside the image, partial tiles."""
+    import bench
+    from test_parity_gpu import _wild_matrices
+
+    B, H, W = 6, 270, 480
+    frames = torch.randint(0, 256, (B, H, W, channels), device=DEV, dtype=torch.uint8)
+    quad = torch.tensor([[0.0, 0.0], [W - 1.0, 0.0], [W - 1.0, H - 1.0], [0.0, H - 1.0]]).expand(B, 4, 2)
+    g = torch.Generator().manual_seed(3)
+    M = bench.perspective_from_quads(quad, quad + 6.0 * torch.randn(B, 4, 2, generator=g)).to(DEV)
+    wild = _wild_matrices(H, W).to(DEV)
+    for mats, size in ((M, (H, W)), (M, (201, 333)), (wild, (H, W))):
+        img = frames[: mats.shape[0]] if mats.shape[0] <= B else frames[:1].expand(mats.shape[0], H, W, channels).contiguous()
+        for ac in (True, False):
+            monkeypatch.setenv("KB200_U8_SIMPLE", "1")
+            want = KT.warp_perspective_from_uint8(img, mats, size, padding_mode=pad, align_corners=ac)
+            monkeypatch.delenv("KB200_U8_SIMPLE")
+            got = KT.warp_perspective_from_uint8(img, mats, size, padding_mode=pad, align_corners=ac)
+            assert torch.equal(got, want), float((got - want).abs().max())
+    rot = KT.get_rotation_matrix2d(torch.tensor([[W / 2, H / 2]], device=DEV).expand(B, 2), torch.linspace(-40, 40, B, device=DEV), torch.ones(B, 2, device=DEV))
+    monkeypatch.setenv("KB200_U8_SIMPLE", "1")
+    want = KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad)
+    monkeypatch.delenv("KB200_U8_SIMPLE")
+    assert torch.equal(KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad), want)

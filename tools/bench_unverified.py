@@ -115,12 +115,17 @@ def ingest():
         got = fused()
         same = torch.equal(got, ref)
         t1 = timed(fused)
+        os.environ["KB200_U8_SIMPLE"] = "1"  # the per-tap kernel (warp_fwd_u8hwc) instead of the tiled one
+        same_simple = torch.equal(fused(), ref)
+        t2 = timed(fused)
     except Exception as exc:
         print(f"{'warp_perspective_from_uint8':34s} FAILED: {exc}")
         return
+    finally:
+        os.environ.pop("KB200_U8_SIMPLE", None)
     gb = B * H * W * 15 / 1e9  # 3 bytes read + 12 written per pixel
-    print(f"{'warp_perspective_from_uint8':34s} permute+float+/255+warp {t0:7.3f} ms | one kernel {t1:7.3f} ms ({gb / t1 / peak * 1e3 * 100:5.1f} % HBM "
-          f"of 15 B/pixel) | x{t0 / t1:4.2f} | {'bit-identical' if same else 'MISMATCH'}")
+    print(f"{'warp_perspective_from_uint8':34s} permute+float+/255+warp {t0:7.3f} ms | tiled kernel {t1:7.3f} ms ({gb / t1 / peak * 1e3 * 100:5.1f} % HBM "
+          f"of 15 B/pixel) x{t0 / t1:4.2f} {'bit-identical' if same else 'MISMATCH'} | per-tap kernel {t2:7.3f} ms {'bit-identical' if same_simple else 'MISMATCH'}")
 
 
 with torch.no_grad():

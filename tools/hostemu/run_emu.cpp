@@ -16,7 +16,7 @@
 #include "../../kornia_b200/csrc/ssim_vwalk.cuh"
 #include "../../kornia_b200/csrc/remap_warp.cuh"
 #include "../../kornia_b200/csrc/warp_bwd_tma2.cuh"
-#include "../../kornia_b200/csrc/warp_u8.cuh"
+#include "../../kornia_b200/csrc/warp_u8_tiled.cuh"
 
 #include <random>
 #include <string>
@@ -33,6 +33,7 @@ alignas(128) unsigned char tma_smem[256 * 1024];
 alignas(128) unsigned char remapw_smem[256 * 1024];
 alignas(128) unsigned char bwd_smem[256 * 1024];
 alignas(128) unsigned char bwd2_smem[256 * 1024];
+alignas(128) unsigned char u8t_smem[256 * 1024];
 void set_error(const char*, ...) {}
 }  // namespace kb200
 
@@ -560,6 +561,44 @@ static void test_u8(int B, int C, int H, int W, int h, int w, bool align, int no
           o1.data(), o2.data(), no);
 }
 
+// warp_u8_tiled_kernel (cooperative byte staging, every byte converted once) against warp_fwd_u8hwc (per-tap conversion):
+// bit for bit, on maps that keep most pixels on the shared-memory path (tame) and on maps that push tiles to the exact path.
+template <int NC, int PAD, bool PROJ, bool ALIGN>
+static void test_u8_tiled(int B, int H, int W, int h, int w, int normalize, bool tame, bool shared_m) {
+  emu::set_smem(u8t_smem, sizeof(u8t_smem));
+  const size_t npix = (size_t)B * H * W, no = (size_t)B * NC * h * w;
+  std::vector<unsigned char> store(npix * NC + 64);
+  unsigned char* bytes = store.data() + ((4 - (reinterpret_cast<uintptr_t>(store.data()) & 3)) & 3);  // 4-byte aligned, as the host requires
+  for (size_t i = 0; i < npix * NC; ++i) bytes[i] = (unsigned char)(rng() & 255);
+  std::vector<float> o1(no, -1.f), o2(no, -2.f), m((size_t)B * 9), bx(w), by(h);
+  for (int i = 0; i < w; ++i) bx[i] = ALIGN || !PROJ ? ((float)i / (float)std::max(w - 1, 1) - 0.5f) * 2.f : ((float)i / (float)std::max(w - 1, 1) - 0.5f) * 2.f;
+  for (int i = 0; i < h; ++i) by[i] = ((float)i / (float)std::max(h - 1, 1) - 0.5f) * 2.f;
+  for (int b = 0; b < B; ++b) {
+    const float t = tame ? 0.01f * (b - 1) : 0.5f * b - 0.3f;
+    const float M[9] = {cosf(t) * (tame ? 1.01f : 1.3f), -sinf(t), tame ? 0.02f * b : 0.4f * b - 0.5f, sinf(t), cosf(t) * (tame ? 0.99f : 0.8f), tame ? -0.01f : 0.3f,
+                        PROJ ? (tame ? 0.004f : 0.08f) : 0.f, PROJ ? (tame ? -0.003f : -0.06f) : 0.f, 1.f};
+    memcpy(&m[(size_t)b * 9], M, sizeof(M));
+  }
+  WarpU8Params u{};
+  u.src = bytes; u.m = m.data(); u.bx = bx.data(); u.by = by.data(); u.fill = nullptr;
+  u.B = B; u.C = NC; u.H = H; u.W = W; u.h = h; u.w = w; u.Bm = shared_m ? 1 : B; u.align = ALIGN; u.normalize = normalize;
+  u.out = o2.data();
+  emu::launch3(dim3(ceil_div(w, GEN_BX), ceil_div(h, GEN_BY), B), dim3(GEN_BX, GEN_BY),
+               [&] { warp_fwd_u8hwc<KB200_BILINEAR, PAD, PROJ ? KIND_PROJ : KIND_AFFINE, NC>(u); });
+  u.out = o1.data();
+  u8t_fast_pixels = u8t_exact_pixels = 0;
+  emu::launch3(dim3(ceil_div(w, 64), ceil_div(h, 32), B), dim3(256), [&] { warp_u8_tiled_kernel<NC, PAD, PROJ, ALIGN>(u); });
+  const int fast_pct = (int)(100 * u8t_fast_pixels / std::max(1ll, u8t_fast_pixels + u8t_exact_pixels));
+  if (tame && fast_pct < 50) {
+    ++failures;
+    printf("FAIL warp_u8_tiled_kernel: only %d %% of the pixels of a near-identity map took the shared-memory path\n", fast_pct);
+  }
+  compare(std::string("warp_u8_tiled_kernel vs warp_fwd_u8hwc ") + (PROJ ? "projective" : "affine") + " pad=" + std::to_string(PAD) + " " + std::to_string(B) + "x" +
+              std::to_string(H) + "x" + std::to_string(W) + "x" + std::to_string(NC) + " -> " + std::to_string(h) + "x" + std::to_string(w) + (ALIGN ? " align" : "") +
+              " normalize=" + std::to_string(normalize) + (tame ? " tame" : " wild") + (shared_m ? " shared matrix" : "") + ", " + std::to_string(fast_pct) + " % from shared memory",
+          o1.data(), o2.data(), no);
+}
+
 static void test_u8_all() {
   int bad = 0;
   for (int v = 0; v < 256; ++v) bad += unit_from_byte((unsigned char)v) != (float)v / 255.0f;
@@ -578,6 +617,15 @@ static void test_u8_all() {
   test_u8<KB200_BICUBIC, KB200_ZEROS, KIND_PROJ>(2, 3, 37, 52, 37, 52, true, 1, false);
   test_u8<KB200_BICUBIC, KB200_REFLECTION, KIND_AFFINE>(2, 4, 19, 23, 33, 40, false, 2, false);
   test_u8<KB200_BICUBIC, KB200_FILL, KIND_PROJ>(1, 3, 16, 16, 20, 24, true, 0, false);
+  test_u8_tiled<3, KB200_ZEROS, true, true>(3, 70, 132, 70, 132, 1, true, false);
+  test_u8_tiled<3, KB200_ZEROS, true, true>(3, 70, 132, 50, 100, 1, false, false);
+  test_u8_tiled<3, KB200_BORDER, true, false>(2, 64, 128, 70, 132, 2, true, false);
+  test_u8_tiled<3, KB200_REFLECTION, false, true>(3, 40, 76, 66, 130, 1, true, true);
+  test_u8_tiled<3, KB200_REFLECTION, true, true>(2, 70, 132, 70, 132, 0, false, false);
+  test_u8_tiled<1, KB200_ZEROS, false, false>(3, 70, 132, 96, 200, 1, true, false);
+  test_u8_tiled<1, KB200_BORDER, true, true>(2, 33, 64, 40, 70, 2, false, false);
+  test_u8_tiled<1, KB200_REFLECTION, false, true>(2, 9, 8, 20, 24, 1, true, false);
+  test_u8_tiled<3, KB200_ZEROS, false, true>(2, 5, 4, 33, 65, 1, true, false);
 }
 
 static void fuzz(int rounds) {
