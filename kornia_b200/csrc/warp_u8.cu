@@ -50,8 +50,8 @@ static int u8_tiled_forward(const WarpU8Params& p, int projective, int interp, i
   const char* simple = getenv("KB200_U8_SIMPLE");
   if (simple && simple[0] == '1') return KB200_EUNSUPPORTED;
   if (interp != KB200_BILINEAR || pad == KB200_FILL || (p.C != 1 && p.C != 3)) return KB200_EUNSUPPORTED;
-  // aligned 32-bit loads of whole in-image words: every image row starts on a 4-byte boundary
-  if (((long long)p.W * p.C) % 4 != 0 || (reinterpret_cast<uintptr_t>(p.src) & 3) != 0) return KB200_EUNSUPPORTED;
+  // aligned 32-bit loads of whole in-image groups of 4 pixels: every image row starts on a 4-byte boundary
+  if (p.W % 4 != 0 || (reinterpret_cast<uintptr_t>(p.src) & 3) != 0) return KB200_EUNSUPPORTED;
   if (p.B > 65535 || ceil_div(p.h, 32) > 65535) return KB200_EUNSUPPORTED;
 #define KB_U8T_CASE(NC_, PAD_)                                                                                             \
   if (p.C == NC_ && pad == PAD_) {                                                                                         \

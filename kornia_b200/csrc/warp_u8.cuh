@@ -37,16 +37,23 @@ constexpr float RCP_255 = 0x1.010102p-8f;  // RN(1/255) = 0x3b808081
 // float(u) / 255.0f, correctly rounded, without the division: q0 = u * RN(1/255) is off by at most one ulp, one residual
 // step repairs it -- e = fma(-255, q0, u) is exact, q = fma(e, r, q0) rounds to the quotient (checked exhaustively over
 // the 256 inputs: tools/hostemu and tests/test_ingest_oracle.py).
-__device__ __forceinline__ float unit_from_byte(unsigned char u) {
-  const float x = (float)u;
+__device__ __forceinline__ float unit_from_level(float x) {  // x = float(byte)
   const float q0 = __fmul_rn(x, RCP_255);
   const float e = __fmaf_rn(-255.0f, q0, x);
   return __fmaf_rn(e, RCP_255, q0);
 }
+__device__ __forceinline__ float unit_from_byte(unsigned char u) { return unit_from_level((float)u); }
 
 // value of a tap: one multiply serves normalize 0 (scale 1, exact) and 1 (scale RN(1/255)); 2 takes the residual step
-__device__ __forceinline__ float value_of_byte(unsigned char u, float scale, bool divide) {
-  return divide ? unit_from_byte(u) : __fmul_rn((float)u, scale);
+__device__ __forceinline__ float value_of_level(float x, float scale, bool divide) {
+  return divide ? unit_from_level(x) : __fmul_rn(x, scale);
+}
+__device__ __forceinline__ float value_of_byte(unsigned char u, float scale, bool divide) { return value_of_level((float)u, scale, divide); }
+
+// float(byte q of word) without the conversion pipe: one PRMT drops the byte into the mantissa of 2^23 (0x4B0000bb =
+// 2^23 + bb exactly), one FADD removes the 2^23 -- both exact, so the result is the I2F's.
+__device__ __forceinline__ float level_of_word_byte(uint32_t word, int q) {
+  return __fadd_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + (unsigned)q)), -8388608.0f);
 }
 
 // NC: channels known at compile time (1 or 3: the loop unrolls, so all C x taps byte loads of a pixel are in flight

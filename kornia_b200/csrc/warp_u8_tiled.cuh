@@ -6,10 +6,11 @@
 //   1. every thread maps its 8 pixels (the reference's coordinate chain, IEEE divisions) and keeps the source
 //      coordinates in registers;
 //   2. the CTA reduces their bounding box (warp shuffles + one shared round) and thread 0 places a 72 x 40 pixel window;
-//   3. all 256 threads stage the window: 32-bit loads of the interleaved bytes (rows of the window are contiguous,
-//      W*C % 4 == 0 and a window start on a multiple of 4 pixels keep every word aligned and on one side of the image
-//      edge), each byte converted ONCE with the tap conversion of warp_u8.cuh and stored to a planar fp32 box in shared
-//      memory -- 1.4 x C conversions per output pixel instead of 4 x C -- out-of-image texels as zeros (= 'zeros' padding);
+//   3. all 256 threads stage the window in groups of 4 pixels: C aligned 32-bit loads of the interleaved bytes (W % 4 == 0
+//      and a window start on a multiple of 4 pixels keep every group aligned and on one side of the image edge), each
+//      byte converted ONCE with the tap conversion of warp_u8.cuh, one 16-byte store per channel into a planar fp32 box
+//      in shared memory -- 1.4 x C conversions per output pixel instead of 4 x C -- out-of-image texels as zeros
+//      (= 'zeros' padding);
 //   4. pixels whose taps lie inside the window blend from shared memory with remap_tiled_kernel's arithmetic, the rest
 //      take the exact per-pixel path of warp_fwd_u8hwc -- bit-identical to that kernel by construction.
 // No TMA: the source is not a tensor the TMA unit could de-interleave AND convert; plain loads, shared stores and two
@@ -49,8 +50,7 @@ __global__ void __launch_bounds__(256, 4) warp_u8_tiled_kernel(const __grid_cons
   constexpr int TW = 64, TH = 32, BW = 72, BH = 40;
   constexpr int NJ = 2, RPW = 4;
   constexpr int PLANE = BW * BH;
-  constexpr int ROW_WORDS = BW * NC / 4;
-  static_assert((BW * NC) % 4 == 0, "whole words per window row");
+  static_assert(BW % 4 == 0, "whole 4-pixel groups per window row");
   constexpr bool INTERIOR = PAD == KB200_REFLECTION;
   constexpr bool PRECLAMP = PAD == KB200_BORDER;
 
@@ -151,28 +151,34 @@ __global__ void __launch_bounds__(256, 4) warp_u8_tiled_kernel(const __grid_cons
   }
   __syncthreads();
 
-  // ---- 3. stage the window: interleaved bytes -> planar fp32, every byte converted once
+  // ---- 3. stage the window: interleaved bytes -> planar fp32, every byte converted once.  Work item = 4 adjacent pixels
+  // of a window row: NC aligned words in (4 * NC bytes; the window starts on a multiple of 4 pixels and W % 4 == 0, so a
+  // group lies entirely inside or outside the image row), one 16-byte shared store per channel plane out.
   const unsigned char* img = p.src + (size_t)b * H * W * NC;
   if (org[2]) {
     const int ox = org[0], oy = org[1];
-    const int row_bytes = W * NC;
-    for (int e = threadIdx.x; e < BH * ROW_WORDS; e += 256) {
-      const int r = e / ROW_WORDS, j = e - r * ROW_WORDS;
-      const int gy = oy + r;
-      const int kb = ox * NC + 4 * j;  // byte offset of this word in image row gy: a multiple of 4, like row_bytes
-      uint32_t word = 0;               // out-of-image texels are zeros ('zeros' padding; never blended otherwise)
-      if ((unsigned)gy < (unsigned)H && kb >= 0 && kb < row_bytes) {
-#ifdef KB200_HOST_EMU
-        if ((reinterpret_cast<uintptr_t>(img + (size_t)gy * row_bytes + kb) & 3) != 0) emu::fail("misaligned 32-bit load of the byte image");
-#endif
-        word = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * row_bytes + kb));
-      }
+    constexpr int GROUPS = BW / 4;  // per window row
+    for (int e = threadIdx.x; e < BH * GROUPS; e += 256) {
+      const int r = e / GROUPS, g = e - r * GROUPS;
+      const int gy = oy + r, gx = ox + 4 * g;
+      uint32_t word[NC];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = 4 * j + q;  // byte within the window row
-        const int pxl = k / NC, c = k - pxl * NC;
-        box[c * PLANE + r * BW + pxl] = value_of_byte((unsigned char)((word >> (8 * q)) & 255u), scale, divide);
+      for (int k = 0; k < NC; ++k) word[k] = 0;  // out-of-image texels are zeros ('zeros' padding; never blended otherwise)
+      if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
+        const unsigned char* src = img + ((size_t)gy * W + gx) * NC;
+#ifdef KB200_HOST_EMU
+        if ((reinterpret_cast<uintptr_t>(src) & 3) != 0 || gx + 4 > W) emu::fail("misaligned or straddling 32-bit loads of the byte image");
+#endif
+#pragma unroll
+        for (int k = 0; k < NC; ++k) word[k] = __ldg(reinterpret_cast<const uint32_t*>(src) + k);
       }
+      float v[NC][4];
+#pragma unroll
+      for (int q = 0; q < 4 * NC; ++q)  // byte q of the group: pixel q / NC, channel q % NC (compile-time after unrolling)
+        v[q % NC][q / NC] = value_of_level(level_of_word_byte(word[q / 4], q % 4), scale, divide);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        *reinterpret_cast<float4*>(box + c * PLANE + r * BW + 4 * g) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
     }
   }
   __syncthreads();

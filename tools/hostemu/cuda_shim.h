@@ -63,6 +63,18 @@ inline int __float_as_int(float f) {
   memcpy(&i, &f, 4);
   return i;
 }
+inline float __uint_as_float(unsigned u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// PRMT in its default mode: result byte i = byte (selector nibble i) of the 8-byte pool {x: 0..3, y: 4..7}
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+  const unsigned long long pool = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((pool >> (8 * ((s >> (4 * i)) & 7))) & 255) << (8 * i);
+  return r;
+}
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 template <typename T>
