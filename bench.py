@@ -400,7 +400,8 @@ def run_ours(args) -> None:
 def run_extra(args) -> None:
     """Secondary BASELINE.json configs (not the driver's headline line): ``--workload blur`` = configs[2]
     gaussian_blur2d k=11 B=256x3x1080x1920; ``--workload warp_bwd`` = configs[3] warp_perspective fwd+bwd
-    (grad wrt image and H) B=128x3x720x1280.  Single GPU, inputs resident, CUDA events, one JSON line."""
+    (grad wrt image and H) B=128x3x720x1280; ``--workload ingest`` = warp_perspective_from_uint8 on B x 1080 x 1920 x 3 decoder
+    bytes (15 algorithmic bytes per pixel).  Single GPU, inputs resident, CUDA events, one JSON line."""
     import kornia_b200 as K
     from kornia_b200 import _lib, _ops
 
@@ -420,6 +421,14 @@ def run_extra(args) -> None:
         pix, bytes_per_pix = B * H_IMG * W_IMG, 24.0
         name = f"gaussian_blur2d k=11 sigma=2 reflect separable B={B}x3x1080x1920"
         tag = "sepfilter_forward"
+    elif args.workload == "ingest":
+        B = args.batch
+        frames = torch.randint(0, 256, (B, H_IMG, W_IMG, 3), device=dev, dtype=torch.uint8)
+        M = make_homographies(B, 1000).to(dev)
+        step = lambda: K.geometry.transform.warp_perspective_from_uint8(frames, M, (H_IMG, W_IMG))  # noqa: E731
+        pix, bytes_per_pix = B * H_IMG * W_IMG, 15.0
+        name = f"warp_perspective_from_uint8 (decoder bytes HWC -> warped fp32 NCHW) B={B}x1080x1920x3, bilinear, zeros"
+        tag = "warp_u8hwc_forward"
     else:
         B, Hh, Ww = min(args.batch, 128), 720, 1280
         src = torch.rand(B, 3, Hh, Ww, device=dev, requires_grad=True)
@@ -477,8 +486,9 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU")
     ap.add_argument("--e2e-chunk", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["warp", "blur", "warp_bwd"], default="warp",
-                    help="warp = the headline (BASELINE.json configs[1]); blur / warp_bwd = configs[2] / configs[3], single GPU")
+    ap.add_argument("--workload", choices=["warp", "blur", "warp_bwd", "ingest"], default="warp",
+                    help="warp = the headline (BASELINE.json configs[1]); blur / warp_bwd = configs[2] / configs[3]; ingest = the uint8 wire-format warp "
+                         "(SURVEY 8f row 4, not a BASELINE config); single GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,7 +1,7 @@
 #!/bin/bash
-# First gpurun call of round 2 (one box, one GPU; budget ~25 min of box time):
+# First gpurun call of round 2 (one box, one GPU; budget ~30-35 min of box time):
 #
-#   /usr/local/graft/bin/gpurun --timeout 1700 -- 'bash tools/r2_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/r2_first_call.sh'
 #
 # Round 1 ended with the GPU budget spent before (a) the wider-caller tests, (b) the kernels of DESIGN.md section 9
 # and (c) the ncu launch list of the final build could run on hardware.  This script collects all of it in one call
@@ -27,7 +27,7 @@ KB200_OPTIN=all timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider
 tail -5 "$OUT/pytest_gpu_optin.log" | tee -a "$OUT/steps.log"
 
 step "3 bench lines (headline, blur, fwd+bwd) and the CPU arm"
-for wl in warp blur warp_bwd; do
+for wl in warp blur warp_bwd ingest; do
   timeout 400 python bench.py --workload $wl > "$OUT/bench_$wl.json" 2> "$OUT/bench_$wl.err"; echo "$wl rc=$?" | tee -a "$OUT/steps.log"
 done
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"
@@ -51,4 +51,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:sepf
   python bench.py --workload blur --batch 16 --steps 1 --warmup 1 --no-cpu-baseline > "$OUT/ncu_blur.log" 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:warp_fwd_tma -s 2 -c 1 -o "$OUT/prof_fwd" \
   python bench.py --batch 64 --steps 1 --warmup 1 --no-cpu-baseline > "$OUT/ncu_fwd.log" 2>&1
+step "7 compute-sanitizer memcheck: default kernels + ingest warps, then the same workload through the opt-in kernels"
+timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py > "$OUT/memcheck_default.txt" 2>&1; tail -3 "$OUT/memcheck_default.txt" | tee -a "$OUT/steps.log"
+KB200_OPTIN=all timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py > "$OUT/memcheck_optin.txt" 2>&1; tail -3 "$OUT/memcheck_optin.txt" | tee -a "$OUT/steps.log"
 ls -la "$OUT" | tee -a "$OUT/steps.log"
