@@ -129,6 +129,15 @@ int kb200_warp_u8hwc_forward(const void* src_u8, const void* m, const void* bx, 
                              int B, int C, int H, int W, int h, int w, int Bm, int projective, int interp, int pad,
                              int align_corners, int normalize, void* stream);
 
+/* undistort_image (calibration/undistort.py:183-198) straight from decoder bytes: image_to_tensor + _to_float32 +
+ * create_meshgrid + distort_points + remap(align_corners=True) in ONE kernel -- the lens model of kb200_undistort_forward
+ * (same (B,16) lens layout, tilt terms must be zero) on the byte loader of kb200_warp_u8hwc_forward (same `normalize`).
+ * src (B,H,W,C) uint8 -> out (B,C,H,W) fp32.  C in {1,3}, W % 4 == 0, 4-byte aligned src; anything else returns
+ * KB200_EUNSUPPORTED and the host converts the image and calls the fp32 path.  Forward only.  Equals
+ * kb200_undistort_forward on the converted image bit for bit.  Status: emulator-verified, not yet run on hardware. */
+int kb200_undistort_u8hwc_forward(const void* src_u8, const void* lens, void* out, int B, int C, int H, int W, int normalize,
+                                  void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * filter2d core (filters/filter.py:136-150: F.pad + view + depthwise F.conv2d + view).
  *   x      (B,C,H,W)

@@ -40,6 +40,7 @@ SIGNATURES = {
     "kb200_remap_backward": (_i, [_vp] * 7 + [_i] * 12 + [_vp]),
     "kb200_undistort_forward": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "kb200_warp_u8hwc_forward": (_i, [_vp] * 6 + [_i] * 12 + [_vp]),
+    "kb200_undistort_u8hwc_forward": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "kb200_filter2d_forward": (_i, [_vp] * 3 + [_i] * 10 + [_vp]),
     "kb200_filter2d_backward_input": (_i, [_vp] * 3 + [_i] * 10 + [_vp]),
     "kb200_filter2d_backward_kernel_workspace_bytes": (_sz, [_i] * 8),

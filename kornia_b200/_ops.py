@@ -151,6 +151,25 @@ def warp_u8hwc(image: torch.Tensor, m: torch.Tensor, bx: torch.Tensor, by: torch
     return out
 
 
+def undistort_u8hwc(image: torch.Tensor, lens: torch.Tensor, normalize: int) -> torch.Tensor:
+    """undistort_image of an interleaved uint8 batch (B,H,W,C) -> planar fp32 (B,C,H,W) in one kernel
+    (kb200_undistort_u8hwc_forward): lens (B,16) as for undistort_fused.  Raises ``_lib.Unsupported`` outside the kernel's
+    envelope (the caller converts the image and takes the fp32 path).  Forward only."""
+    _require_cuda(image, "image")
+    if image.dtype != torch.uint8:
+        raise RuntimeError(f"kornia_b200: expected a uint8 image, got {image.dtype}")
+    img = image.contiguous()
+    ln = lens.to(device=image.device, dtype=torch.float32).contiguous()
+    B, H, W, C = img.shape
+    out = torch.empty((B, C, H, W), device=image.device, dtype=torch.float32)
+    if out.numel() == 0:
+        raise _lib.Unsupported("empty image")
+    with torch.cuda.device(image.device), _Timed("undistort_u8hwc_forward", image):
+        _lib.call("kb200_undistort_u8hwc_forward", _ptr(img), _ptr(ln), _ptr(out), B, C, H, W, int(normalize), _stream(image))
+    _bump()
+    return out
+
+
 class RemapFunction(torch.autograd.Function):
     """out = sample(image, (map_x, map_y)); differentiable w.r.t. the image and both maps."""
 

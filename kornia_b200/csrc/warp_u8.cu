@@ -33,10 +33,10 @@ static int launch_u8(const WarpU8Params& p, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- tiled kernel (warp_u8_tiled.cuh)
-template <int NC, int PAD, bool PROJ, bool ALIGN>
+template <int NC, int PAD, int KIND, bool ALIGN>
 static int launch_u8_tiled(const WarpU8Params& p, cudaStream_t st) {
   const dim3 grid(ceil_div(p.w, 64), ceil_div(p.h, 32), p.B);
-  warp_u8_tiled_kernel<NC, PAD, PROJ, ALIGN><<<grid, 256, U8T_SMEM_BYTES(NC), st>>>(p);
+  warp_u8_tiled_kernel<NC, PAD, KIND, ALIGN><<<grid, 256, U8T_SMEM_BYTES(NC), st>>>(p);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("warp_u8hwc_forward (tiled): kernel launch failed: %s", cudaGetErrorString(e));
@@ -55,8 +55,8 @@ static int u8_tiled_forward(const WarpU8Params& p, int projective, int interp, i
   if (p.B > 65535 || ceil_div(p.h, 32) > 65535) return KB200_EUNSUPPORTED;
 #define KB_U8T_CASE(NC_, PAD_)                                                                                             \
   if (p.C == NC_ && pad == PAD_) {                                                                                         \
-    if (projective) return p.align ? launch_u8_tiled<NC_, PAD_, true, true>(p, st) : launch_u8_tiled<NC_, PAD_, true, false>(p, st);  \
-    return p.align ? launch_u8_tiled<NC_, PAD_, false, true>(p, st) : launch_u8_tiled<NC_, PAD_, false, false>(p, st);     \
+    if (projective) return p.align ? launch_u8_tiled<NC_, PAD_, KIND_PROJ, true>(p, st) : launch_u8_tiled<NC_, PAD_, KIND_PROJ, false>(p, st);  \
+    return p.align ? launch_u8_tiled<NC_, PAD_, KIND_AFFINE, true>(p, st) : launch_u8_tiled<NC_, PAD_, KIND_AFFINE, false>(p, st);     \
   }
   KB_U8T_CASE(3, KB200_ZEROS)
   KB_U8T_CASE(3, KB200_BORDER)
@@ -114,4 +114,21 @@ int kb200_warp_u8hwc_forward(const void* src, const void* m, const void* bx, con
   const int rc = u8_tiled_forward(p, projective, interp, pad, st);
   if (rc != KB200_EUNSUPPORTED) return rc;
   return projective ? by_interp<KIND_PROJ>(p, interp, pad, st) : by_interp<KIND_AFFINE>(p, interp, pad, st);
+}
+
+int kb200_undistort_u8hwc_forward(const void* src, const void* lens, void* out, int B, int C, int H, int W, int normalize, void* stream) {
+  KB_CHECK_ARG(src && lens && out, "null pointer argument");
+  KB_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "non-positive shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  KB_CHECK_ARG((long long)H * W < (1ll << 31), "plane too large for 32-bit in-plane offsets");
+  KB_CHECK_ARG(normalize >= 0 && normalize <= 2, "normalize must be 0 (raw), 1 (times 1/255) or 2 (divided by 255), got %d", normalize);
+  // the tiled kernel is the only form: anything else is declined and the host converts + calls the fp32 path
+  if ((C != 1 && C != 3) || W % 4 != 0 || (reinterpret_cast<uintptr_t>(src) & 3) != 0 || B > 65535 || ceil_div(H, 32) > 65535) {
+    set_error("undistort_u8hwc_forward: needs C in {1,3}, W %% 4 == 0 and a 4-byte aligned image");
+    return KB200_EUNSUPPORTED;
+  }
+  WarpU8Params p{};
+  p.src = (const unsigned char*)src; p.lens = (const float*)lens; p.out = (float*)out;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.h = H; p.w = W; p.Bm = B; p.align = 1; p.normalize = normalize;
+  cudaStream_t st = (cudaStream_t)stream;
+  return C == 3 ? launch_u8_tiled<3, KB200_ZEROS, U8_KIND_LENS, true>(p, st) : launch_u8_tiled<1, KB200_ZEROS, U8_KIND_LENS, true>(p, st);
 }

@@ -26,6 +26,7 @@ struct WarpU8Params {
   float* out;                // (B,C,h,w) planar
   int B, C, H, W, h, w, Bm, align;
   int normalize;             // value of a byte u: 0 float(u); 1 float(u) * RN(1/255); 2 float(u) / 255 (see below)
+  const float* lens;         // undistort only (warp_u8_tiled.cuh, U8_KIND_LENS): (B,16) lens numbers, m / bx / by unused
 };
 
 // `image.float() / 255.0` (io.py:111) is evaluated differently by torch's two backends: the CPU kernel divides, the CUDA

@@ -20,7 +20,7 @@
 // Status: written after the round-1 GPU budget was spent; compiled for sm_100a, executed on the emulator, not yet run on
 // hardware.  KB200_U8_SIMPLE=1 forces warp_fwd_u8hwc (tests compare the two bit for bit).
 #pragma once
-#include "warp_tma.cuh"
+#include "remap_tiled.cuh"
 #include "warp_u8.cuh"
 
 namespace kb200 {
@@ -44,8 +44,14 @@ __device__ __noinline__ void u8_exact_pixel(const unsigned char* img, int H, int
 static long long u8t_fast_pixels = 0, u8t_exact_pixels = 0;  // tools/hostemu reports the share of the shared-memory path
 #endif
 
-template <int NC, int PAD, bool PROJ, bool ALIGN>
-__global__ void __launch_bounds__(256, 4) warp_u8_tiled_kernel(const __grid_constant__ WarpU8Params p) {
+// Coordinate source of the tile kernel: the affine / projective map of the warps (KIND_AFFINE, KIND_PROJ of
+// warp_generic.cuh) or U8_KIND_LENS -- undistort_image (calibration/undistort.py:183-198) on decoder bytes: the lens model
+// of remap_tiled.cuh:lens_distort evaluated per pixel, then remap's normalise -> unnormalise chain (align_corners=True),
+// exactly as remap_tiled_kernel<NC, ZEROS, true, LENS=true> does on an fp32 image; output size = input size.
+constexpr int U8_KIND_LENS = 3;
+
+template <int NC, int PAD, int KIND, bool ALIGN>
+__global__ void __launch_bounds__(256, KIND == U8_KIND_LENS ? 3 : 4) warp_u8_tiled_kernel(const __grid_constant__ WarpU8Params p) {
   using R = RN<float>;
   constexpr int TW = 64, TH = 32, BW = 72, BH = 40;
   constexpr int NJ = 2, RPW = 4;
@@ -68,7 +74,15 @@ __global__ void __launch_bounds__(256, 4) warp_u8_tiled_kernel(const __grid_cons
   const size_t oplane = (size_t)p.h * p.w;
   const int x0 = tx * TW + lane, y_base = ty * TH + warp * RPW;
   Mat3<float> m;
-  m.load(p.m + (p.Bm == 1 ? 0 : (size_t)b * 9));
+  float L[16];
+  if (KIND == U8_KIND_LENS) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) L[k] = __ldg(p.lens + (size_t)b * 16 + k);
+  } else {
+    m.load(p.m + (p.Bm == 1 ? 0 : (size_t)b * 9));
+  }
+  // conversions.py:1487-1498 (remap's pixel -> [-1,1] step): factor = 2 / clamp(size - 1, eps)
+  const float nfx = R::div(2.f, fmaxf(Wm1, 1e-8f)), nfy = R::div(2.f, fmaxf(Hm1, 1e-8f));
   const float scale = p.normalize == 1 ? RCP_255 : 1.0f;
   const bool divide = p.normalize == 2;
 
@@ -78,18 +92,26 @@ __global__ void __launch_bounds__(256, 4) warp_u8_tiled_kernel(const __grid_cons
   bool finite = true;
   float bxv[NJ];
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) bxv[j] = x0 + 32 * j < p.w ? ldg(p.bx + x0 + 32 * j) : 0.f;
+  for (int j = 0; j < NJ; ++j) bxv[j] = (KIND != U8_KIND_LENS && x0 + 32 * j < p.w) ? ldg(p.bx + x0 + 32 * j) : 0.f;
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
     const int y = y_base + i;
-    const float byv = y < p.h ? ldg(p.by + y) : 0.f;
+    const float byv = (KIND != U8_KIND_LENS && y < p.h) ? ldg(p.by + y) : 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int x = x0 + 32 * j;
       const int u = i * NJ + j;
       float gx = 0.f, gy = 0.f, den;
       const bool live = x < p.w && y < p.h;
-      if (live) map_point<float, PROJ>(m, bxv[j], byv, gx, gy, den);
+      if (live) {
+        if (KIND == U8_KIND_LENS) {
+          lens_distort(L, (float)x, (float)y, gx, gy);
+          gx = R::sub(R::mul(nfx, gx), 1.f);
+          gy = R::sub(R::mul(nfy, gy), 1.f);
+        } else {
+          map_point<float, KIND == KIND_PROJ>(m, bxv[j], byv, gx, gy, den);
+        }
+      }
       ux[u] = unnorm<ALIGN>(gx, Wm1, Wf);
       uy[u] = unnorm<ALIGN>(gy, Hm1, Hf);
       if (live) {

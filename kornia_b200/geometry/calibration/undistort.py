@@ -15,7 +15,7 @@ from ... import _lib, _ops
 from ..transform.imgwarp import remap
 from .distort import distort_points
 
-__all__ = ["undistort_image"]
+__all__ = ["undistort_image", "undistort_image_from_uint8"]
 
 
 def _fused_request(image: torch.Tensor, K: torch.Tensor, dist: torch.Tensor, B: int):
@@ -82,3 +82,40 @@ def undistort_image(image: torch.Tensor, K: torch.Tensor, dist: torch.Tensor) ->
     map_y = seen_at[..., 1].reshape(B, rows, cols)
     out = remap(image.reshape(B, channels, rows, cols), map_x, map_y, align_corners=True)
     return out.view_as(image)
+
+
+@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
+def undistort_image_from_uint8(image: torch.Tensor, K: torch.Tensor, dist: torch.Tensor, normalize=True) -> torch.Tensor:
+    """``undistort_image(image_to_tensor(image).float() / 255, K, dist)`` for a decoder's uint8 ``image`` (B,H,W,C) or
+    (H,W,C) -> fp32 (B,C,H,W) (the wire format and the maps fused).  One kernel
+    (kb200_undistort_u8hwc_forward: bytes staged and converted once per window, lens model per pixel, no maps) when no
+    gradient is asked for, the tilt coefficients are zero, C is 1 or 3 and W % 4 == 0; otherwise the image is converted
+    and ``undistort_image`` runs (differentiable w.r.t. ``K`` and ``dist``).  ``normalize`` as in
+    ``warp_perspective_from_uint8``: True / "device" (times 1/255, torch's CUDA ``x / 255.0``), "exact" (divided), False.
+
+    Status: the kernel has run on the host emulator only."""
+    from ..transform.ingest import _batched_hwc, _normalize_code
+
+    image = _batched_hwc(image)
+    if K.shape[-2:] != (3, 3):
+        raise ValueError(f"K matrix shape is invalid. Got {K.shape}.")
+    if dist.shape[-1] not in (4, 5, 8, 12, 14):
+        raise ValueError(f"Invalid number of distortion coefficients. Got {dist.shape[-1]}.")
+    norm = _normalize_code(normalize)
+    B = image.shape[0]
+    needs_grad = torch.is_grad_enabled() and (K.requires_grad or dist.requires_grad)
+    if image.is_cuda and not needs_grad:
+        lens = pack_lens(K, dist, torch.empty(0, device=image.device, dtype=torch.float32))
+        if lens is not None and lens.shape[0] in (1, B):  # one camera for the whole batch, or one per image
+            try:
+                return _ops.undistort_u8hwc(image, lens.expand(B, 16), norm)
+            except _lib.Unsupported:
+                pass
+    x = image.permute(0, 3, 1, 2).float()
+    if norm == 1:
+        x = x / 255.0  # on a CUDA device: times the fp32 reciprocal (the form the kernel reproduces)
+    elif norm == 2:
+        x = torch.div(x, torch.tensor(255.0, device=x.device))  # a tensor divisor keeps the true division on every backend
+    Kb = K if K.dim() == 3 else K.expand(B, 3, 3)
+    db = dist if dist.dim() == 2 else dist.expand(B, dist.shape[-1])
+    return undistort_image(x.contiguous(), Kb, db)

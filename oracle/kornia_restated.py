@@ -657,3 +657,12 @@ def warp_affine_from_uint8(image, M, dsize, mode="bilinear", padding_mode="zeros
                            normalize=True):
     """image_to_tensor, _to_float32, warp_affine (imgwarp.py:177)."""
     return warp_affine(image_to_float(image, normalize), M, dsize, mode, padding_mode, align_corners, fill_value)
+
+
+def undistort_image_from_uint8(image, K, dist, normalize=True):
+    """image_to_tensor, _to_float32, undistort_image (calibration/undistort.py:138-198)."""
+    x = image_to_float(image, normalize)
+    B = x.shape[0]
+    Kb = K if K.dim() == 3 else K.expand(B, 3, 3)
+    db = dist if dist.dim() == 2 else dist.expand(B, dist.shape[-1])
+    return undistort_image(x, Kb, db)

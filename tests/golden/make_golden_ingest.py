@@ -74,6 +74,32 @@ def main():
     add("affine_fill_scalar", img3, rot, dict(dsize=[H, W], mode="bilinear", padding_mode="fill", align_corners=True), True, fill=torch.tensor(0.5))
     add("affine_fill_gray", frames(B, H, W, 1), rot, dict(dsize=[H, W], mode="bilinear", padding_mode="fill", align_corners=False), True,
         fill=torch.tensor([0.3]))
+    # ------------------------------------------------------------------ undistort_image on decoder bytes
+    import kornia.geometry.calibration as KC
+
+    def undist(name, image, cam, coef, normalize=True):
+        x = K.image.image_to_tensor(image.numpy(), keepdim=False)
+        x = _to_float32(x) if normalize else x.float()
+        n = x.shape[0]
+        out = KC.undistort_image(x, cam if cam.dim() == 3 else cam.expand(n, 3, 3), coef if coef.dim() == 2 else coef.expand(n, coef.shape[-1]))
+        bag.add(name, "undistort_image_from_uint8", dict(image=image, K=cam, dist=coef), {} if normalize else dict(normalize=False), dict(out=out))
+
+    Hu, Wu = 30, 40
+    fr = frames(2, Hu, Wu, 3)
+    cam = torch.tensor([[[34.0, 0.0, 19.5], [0.0, 33.0, 14.0], [0.0, 0.0, 1.0]], [[30.0, 0.0, 21.0], [0.0, 31.0, 15.5], [0.0, 0.0, 1.0]]])
+    coefs = {4: torch.tensor([[-0.25, 0.08, 0.002, -0.003], [0.15, -0.05, -0.004, 0.001]]),
+             5: torch.tensor([[-0.25, 0.08, 0.002, -0.003, 0.01], [0.15, -0.05, -0.004, 0.001, -0.02]]),
+             8: torch.tensor([[-0.25, 0.08, 0.002, -0.003, 0.01, 0.04, -0.02, 0.004], [0.15, -0.05, -0.004, 0.001, -0.02, 0.03, 0.01, -0.002]]),
+             12: torch.tensor([[-0.25, 0.08, 0.002, -0.003, 0.01, 0.04, -0.02, 0.004, 0.003, -0.001, 0.002, 0.0015],
+                               [0.15, -0.05, -0.004, 0.001, -0.02, 0.03, 0.01, -0.002, -0.002, 0.001, 0.001, -0.001]])}
+    coefs[14] = torch.cat([coefs[12], torch.tensor([[0.02, -0.015], [-0.01, 0.02]])], -1)   # tilt terms: the composition path
+    for k, c in coefs.items():
+        undist(f"undistort_u8_{k}", fr, cam, c)
+    undist("undistort_u8_raw", fr, cam, coefs[5], normalize=False)
+    undist("undistort_u8_gray", frames(2, Hu, Wu, 1), cam, coefs[8])
+    undist("undistort_u8_single_hwc", fr[0], cam[:1], coefs[5][:1])
+    undist("undistort_u8_shared_camera", fr, cam[0], coefs[5][0])
+    undist("undistort_u8_odd_width", frames(1, 21, 37, 3), cam[:1], coefs[4][:1])    # W % 4 != 0: the composition path
     bag.save(os.path.join(HERE, "ingest.npz"))
 
 

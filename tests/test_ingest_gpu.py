@@ -17,10 +17,12 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("KB200_RUN_UNVERIFIED") != "1", reason="unverified device code: set KB200_RUN_UNVERIFIED=1")]
 DEV = "cuda"
 ING = golden("ingest")
-KT = K.geometry.transform
+KT, KC = K.geometry.transform, K.geometry.calibration
+WARPS = [n for n in ING.names() if ING.meta[n]["op"].startswith("warp_")]
+UNDISTORT = [n for n in ING.names() if ING.meta[n]["op"].startswith("undistort")]
 
 
-@pytest.mark.parametrize("name", ING.names())
+@pytest.mark.parametrize("name", WARPS)
 def test_ingest_matches_reference(name):
     """Golden vectors of image_to_tensor + _to_float32 + warp_* recorded from the reference on CPU: 1e-4 rel (north_star)."""
     op, kw, ins, outs = ING.case(name)
@@ -36,7 +38,7 @@ def test_ingest_matches_reference(name):
         torch.testing.assert_close(got.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("name", ING.names())
+@pytest.mark.parametrize("name", WARPS)
 def test_ingest_is_bit_identical_to_the_three_steps_on_device(name):
     """Same device, same sampler arithmetic: permute + .float() / 255 + the fp32 warp of this library == one kernel."""
     op, kw, ins, outs = ING.case(name)
@@ -115,3 +117,50 @@ def test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(monkeypatch,
     want = KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad)
     monkeypatch.delenv("KB200_U8_SIMPLE")
     assert torch.equal(KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad), want)
+
+
+@pytest.mark.parametrize("name", UNDISTORT)
+def test_undistort_from_bytes_matches_reference_and_the_fp32_path(monkeypatch, name):
+    """Golden vectors of image_to_tensor + _to_float32 + undistort_image from the reference (1e-4 rel); on the device: close to
+    convert + undistort_image through the default maps + remap path, and EQUAL to convert + the fused fp32 undistort
+    (KB200_FUSED_UNDISTORT=1), whose lens arithmetic the byte kernel shares."""
+    op, kw, ins, outs = ING.case(name)
+    monkeypatch.delenv("KB200_FUSED_UNDISTORT", raising=False)
+    before = K._ops.launch_count
+    got = run_family_case(KC, op, kw, ins, device=DEV)
+    img = ins["image"]
+    one_kernel = ins["dist"].shape[-1] != 14 and img.shape[-1] in (1, 3) and img.shape[-2] % 4 == 0
+    assert (K._ops.launch_count == before + 1) == one_kernel
+    assert got.device.type == torch.device(DEV).type and got.dtype == torch.float32 and got.shape == outs["out"].shape and got.is_contiguous()
+    torch.testing.assert_close(got.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
+    x = img.to(DEV)
+    x = (x.unsqueeze(0) if x.dim() == 3 else x).permute(0, 3, 1, 2).float()
+    x = (x / 255.0 if kw.get("normalize", True) else x).contiguous()
+    n = x.shape[0]
+    cam, d = ins["K"].to(DEV), ins["dist"].to(DEV)
+    cam, d = (cam if cam.dim() == 3 else cam.expand(n, 3, 3).contiguous()), (d if d.dim() == 2 else d.expand(n, d.shape[-1]).contiguous())
+    torch.testing.assert_close(got, KC.undistort_image(x, cam, d), rtol=1e-4, atol=1e-5)
+    if one_kernel:
+        monkeypatch.setenv("KB200_FUSED_UNDISTORT", "1")
+        assert torch.equal(got, KC.undistort_image(x, cam, d))
+
+
+def test_undistort_from_bytes_full_size():
+    """1080p: zero coefficients return byte / 255 to the accuracy of the (p - c) / f * f + c round trip; a real lens equals the
+    fp32 path on the converted frames to 1e-5 rel-L2; gradients w.r.t. the camera take the differentiable composition."""
+    from helpers import rel_l2
+
+    B, H, W = 2, 1080, 1920
+    frames = torch.randint(0, 256, (B, H, W, 3), device=DEV, dtype=torch.uint8)
+    cam = torch.tensor([[1500.0, 0.0, 960.0], [0.0, 1500.0, 540.0], [0.0, 0.0, 1.0]], device=DEV).expand(B, 3, 3).contiguous()
+    x = (frames.permute(0, 3, 1, 2).float() / 255.0).contiguous()
+    torch.testing.assert_close(KC.undistort_image_from_uint8(frames, cam, torch.zeros(B, 4, device=DEV)), x, rtol=0, atol=2e-3)
+    dist = torch.tensor([[-0.2, 0.05, 0.001, -0.002, 0.01]], device=DEV).expand(B, 5).contiguous()
+    before = K._ops.launch_count
+    got = KC.undistort_image_from_uint8(frames, cam, dist)
+    assert K._ops.launch_count == before + 1
+    assert rel_l2(got, KC.undistort_image(x, cam, dist)) < 1e-5
+    camg = cam.clone().requires_grad_(True)
+    out = KC.undistort_image_from_uint8(frames[:, :64, :64].contiguous(), camg, dist)
+    (g,) = torch.autograd.grad(out.sum(), [camg])
+    assert g.shape == cam.shape and bool(torch.isfinite(g).all())

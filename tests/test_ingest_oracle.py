@@ -18,6 +18,10 @@ ING = golden("ingest")
 FP32 = dict(rtol=1e-4, atol=1e-5)
 
 
+def product_module(op):
+    return K.geometry.calibration if op.startswith("undistort") else K.geometry.transform
+
+
 @pytest.mark.parametrize("name", ING.names())
 def test_oracle_matches_reference(name):
     op, kw, ins, outs = ING.case(name)
@@ -46,11 +50,32 @@ def device_call_on_cpu(monkeypatch):
 
     monkeypatch.setattr(_ops, "warp_u8hwc", mirror)
 
+    def undistort_mirror(image, lens, normalize):
+        """kb200_undistort_u8hwc_forward's contract on CPU: (B,16) lens rows -> camera matrix + 12 coefficients -> the oracle."""
+        assert image.dtype == torch.uint8 and image.dim() == 4 and lens.shape == (image.shape[0], 16) and normalize in (0, 1, 2)
+        cam = torch.zeros(lens.shape[0], 3, 3)
+        cam[:, 0, 0], cam[:, 1, 1], cam[:, 0, 2], cam[:, 1, 2], cam[:, 2, 2] = lens[:, 0], lens[:, 1], lens[:, 2], lens[:, 3], 1.0
+        if image.shape[-1] not in (1, 3) or image.shape[2] % 4 != 0:
+            raise _ops._lib.Unsupported("outside the tiled kernel's envelope")
+        return R.undistort_image(R.image_to_float(image, normalize != 0), cam, lens[:, 4:].contiguous())
+
+    from kornia_b200.geometry.calibration import undistort
+
+    monkeypatch.setattr(_ops, "undistort_u8hwc", undistort_mirror)
+    monkeypatch.setattr(undistort, "remap", R.remap)                              # the composition path (tilt, odd widths)
+
+    def take_the_kernel_path():  # undistort only: its host code asks image.is_cuda before calling the C entry
+        monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+
+    return take_the_kernel_path
+
 
 @pytest.mark.parametrize("name", ING.names())
 def test_product_host_logic_on_cpu(device_call_on_cpu, name):
     op, kw, ins, outs = ING.case(name)
-    got = run_family_case(K.geometry.transform, op, kw, ins)
+    if op.startswith("undistort"):
+        device_call_on_cpu()
+    got = run_family_case(product_module(op), op, kw, ins)
     torch.testing.assert_close(got, outs["out"], **FP32)
 
 
@@ -107,3 +132,20 @@ def test_byte_conversions():
     want = (torch.arange(256, dtype=torch.uint8).float() / 255.0).numpy()
     assert np.array_equal(q, want) and not np.array_equal(q0, want)
     assert np.abs(q0.view(np.int32) - want.view(np.int32)).max() == 1
+
+
+def test_undistort_from_uint8_contract(monkeypatch):
+    f = K.geometry.calibration.undistort_image_from_uint8
+    img, cam, d = torch.zeros(2, 8, 12, 3, dtype=torch.uint8), torch.eye(3).expand(2, 3, 3), torch.zeros(2, 5)
+    with pytest.raises(TypeError):
+        f(img.float(), cam, d)
+    with pytest.raises(ValueError):
+        f(img, cam[:, :2], d)
+    with pytest.raises(ValueError):
+        f(img, cam, torch.zeros(2, 6))
+    with pytest.raises(ValueError, match="normalize"):
+        f(img, cam, d, normalize=255)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        f(img, cam, d)  # valid request, CPU tensors: no CPU path
+    a, b = inspect.signature(f), inspect.signature(K.geometry.calibration.undistort_image)
+    assert list(a.parameters)[:-1] == list(b.parameters) and list(a.parameters)[-1] == "normalize"

@@ -587,7 +587,7 @@ static void test_u8_tiled(int B, int H, int W, int h, int w, int normalize, bool
                [&] { warp_fwd_u8hwc<KB200_BILINEAR, PAD, PROJ ? KIND_PROJ : KIND_AFFINE, NC>(u); });
   u.out = o1.data();
   u8t_fast_pixels = u8t_exact_pixels = 0;
-  emu::launch3(dim3(ceil_div(w, 64), ceil_div(h, 32), B), dim3(256), [&] { warp_u8_tiled_kernel<NC, PAD, PROJ, ALIGN>(u); });
+  emu::launch3(dim3(ceil_div(w, 64), ceil_div(h, 32), B), dim3(256), [&] { warp_u8_tiled_kernel<NC, PAD, PROJ ? KIND_PROJ : KIND_AFFINE, ALIGN>(u); });
   const int fast_pct = (int)(100 * u8t_fast_pixels / std::max(1ll, u8t_fast_pixels + u8t_exact_pixels));
   if (tame && check_share && fast_pct < 50) {
     ++failures;
@@ -597,6 +597,44 @@ static void test_u8_tiled(int B, int H, int W, int h, int w, int normalize, bool
               std::to_string(H) + "x" + std::to_string(W) + "x" + std::to_string(NC) + " -> " + std::to_string(h) + "x" + std::to_string(w) + (ALIGN ? " align" : "") +
               " normalize=" + std::to_string(normalize) + (tame ? " tame" : " wild") + (shared_m ? " shared matrix" : "") + ", " + std::to_string(fast_pct) + " % from shared memory",
           o1.data(), o2.data(), no);
+}
+
+// undistort_image from decoder bytes (warp_u8_tiled_kernel<U8_KIND_LENS>) against the fp32 fused undistort
+// (remap_tiled_kernel<LENS>, itself checked against maps + remap above) on the image the reference would have converted first.
+template <int NC>
+static void test_u8_undistort(int B, int H, int W, int normalize, bool strong) {
+  const size_t npix = (size_t)B * H * W, n = npix * NC;
+  std::vector<unsigned char> store(n + 64);
+  unsigned char* bytes = store.data() + ((4 - (reinterpret_cast<uintptr_t>(store.data()) & 3)) & 3);
+  for (size_t i = 0; i < n; ++i) bytes[i] = (unsigned char)(rng() & 255);
+  std::vector<float> ss, o1(n, -1.f), o2(n, -2.f), lens((size_t)B * 16);
+  float* planar = aligned(ss, n);
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < NC; ++c)
+      for (int i = 0; i < H * W; ++i) {
+        const float f = (float)bytes[((size_t)b * H * W + i) * NC + c];
+        planar[((size_t)b * NC + c) * H * W + i] = normalize == 2 ? f / 255.0f : normalize == 1 ? f * (1.0f / 255.0f) : f;
+      }
+  for (int b = 0; b < B; ++b) {
+    const float L[16] = {(strong ? 0.35f : 0.8f) * W + 3 * b, (strong ? 0.3f : 0.75f) * W, 0.5f * W - 3.f, 0.5f * H + 2.f, strong ? -0.45f : -0.21f, 0.07f, 0.002f, -0.003f, 0.01f, 0.04f, -0.02f, 0.004f, 0.003f, -0.001f, 0.002f, 0.0015f};
+    memcpy(&lens[(size_t)b * 16], L, sizeof(L));
+  }
+  const dim3 grid(ceil_div(W, 64), ceil_div(H, 32), B);
+  emu::lazy_tma = false;
+  emu::set_smem(remap_smem, sizeof(remap_smem));
+  const CUtensorMap map = emu::make_map(planar, W, H, B * NC, 72, 40, NC);
+  RemapTiledParams rp{planar, nullptr, nullptr, o2.data(), B, H, W, H, W, B, 0, lens.data()};
+  emu::launch3(grid, dim3(256), [&] { remap_tiled_kernel<NC, KB200_ZEROS, true, true>(map, rp); });
+  emu::set_smem(u8t_smem, sizeof(u8t_smem));
+  WarpU8Params u{};
+  u.src = bytes; u.lens = lens.data(); u.out = o1.data();
+  u.B = B; u.C = NC; u.H = H; u.W = W; u.h = H; u.w = W; u.Bm = B; u.align = 1; u.normalize = normalize;
+  u8t_fast_pixels = u8t_exact_pixels = 0;
+  emu::launch3(grid, dim3(256), [&] { warp_u8_tiled_kernel<NC, KB200_ZEROS, U8_KIND_LENS, true>(u); });
+  compare("warp_u8_tiled_kernel<LENS> (undistort from bytes) vs convert + remap_tiled_kernel<LENS> " + std::to_string(B) + "x" + std::to_string(H) + "x" +
+              std::to_string(W) + "x" + std::to_string(NC) + " normalize=" + std::to_string(normalize) + (strong ? " strong" : "") + ", " +
+              std::to_string((int)(100 * u8t_fast_pixels / std::max(1ll, u8t_fast_pixels + u8t_exact_pixels))) + " % from shared memory",
+          o1.data(), o2.data(), n);
 }
 
 static void test_u8_all() {
@@ -628,6 +666,9 @@ static void test_u8_all() {
   test_u8_tiled<1, KB200_BORDER, true, true>(2, 33, 64, 40, 70, 2, false, false);
   test_u8_tiled<1, KB200_REFLECTION, false, true>(2, 9, 8, 20, 24, 1, true, false);
   test_u8_tiled<3, KB200_ZEROS, false, true>(2, 5, 4, 33, 65, 1, true, false);
+  test_u8_undistort<3>(2, 70, 132, 1, false);
+  test_u8_undistort<3>(2, 97, 200, 2, true);
+  test_u8_undistort<1>(1, 33, 64, 0, false);
 }
 
 static void fuzz(int rounds) {
