@@ -677,7 +677,7 @@ static void fuzz(int rounds) {
   for (int r = 0; r < rounds; ++r) {
     const int H = pick(1, 110), W = 4 * pick(1, 70), planes = pick(1, 4), lazy = pick(0, 1);
     const unsigned grid = (unsigned)pick(1, 9);
-    switch (pick(0, 21)) {
+    switch (pick(0, 22)) {
       case 10: if (H > 1 && W > 1) test_filter2d<3, KB200_REFLECT>(planes, H, W, grid, lazy); break;
       case 11: if (H > 3 && W > 3) test_filter2d<7, KB200_REPLICATE>(planes, H, W, grid, lazy); break;
       case 12: test_filter2d<7, KB200_CONSTANT>(planes, H, W, grid, lazy); break;
@@ -690,6 +690,7 @@ static void fuzz(int rounds) {
       case 19: test_u8_tiled<3, KB200_BORDER, false, false>(pick(1, 3), H, W, pick(1, 80), pick(1, 150), pick(0, 2), pick(0, 1), pick(0, 1), false); break;
       case 20: test_u8_tiled<1, KB200_REFLECTION, true, false>(pick(1, 3), H, W, H, W, pick(0, 2), pick(0, 1), false, false); break;
       case 21: test_u8_tiled<3, KB200_REFLECTION, true, true>(pick(1, 2), H, W, std::max(1, H - pick(0, 5)), W, pick(0, 2), pick(0, 1), false, false); break;
+      case 22: if (H > 1) test_u8_undistort<3>(pick(1, 2), H, W, pick(0, 2), pick(0, 1)); break;
       case 0: if (H > 5 && W > 5) test_sepfilter<11, KB200_REFLECT>(1, planes, H, W, grid, lazy); break;
       case 1: if (H > 8 && W > 8) test_sepfilter<17, KB200_REPLICATE>(1, planes, H, W, grid, lazy); break;
       case 2: test_sepfilter<5, KB200_CONSTANT>(planes, 1, H, W, grid, lazy); break;
