@@ -204,3 +204,24 @@ def test_c_abi_validation_of_the_caller_entry_points():
     assert lib.kb200_perspective_from_points(p8, p8, None, 4, 0, 4, None) == -1
     assert lib.kb200_perspective_from_points(p8, p8, p8, 4, 3, 4, None) == -1 and b"bad dtype" in lib.kb200_last_error()
     assert isinstance(lib.kb200_last_warp_launches(), int)
+
+
+def test_c_abi_validation_of_the_wire_format_entry_points():
+    """kb200_warp_u8hwc_forward / kb200_undistort_u8hwc_forward refuse bad requests on the host, before any CUDA call."""
+    lib = _lib.load()
+    p8 = ctypes.c_void_p(8)  # non-null dummy; never dereferenced on these paths
+    warp = lib.kb200_warp_u8hwc_forward
+    #            src m   bx  by  fill out B  C  H  W  h  w  Bm proj interp pad align normalize stream
+    assert warp(None, p8, p8, p8, None, p8, 2, 3, 8, 8, 8, 8, 2, 1, 0, 0, 1, 1, None) == -1 and b"null pointer" in lib.kb200_last_error()
+    assert warp(p8, p8, p8, p8, None, p8, 0, 3, 8, 8, 8, 8, 0, 1, 0, 0, 1, 1, None) == -1 and b"non-positive shape" in lib.kb200_last_error()
+    assert warp(p8, p8, p8, p8, None, p8, 2, 3, 8, 8, 8, 8, 3, 1, 0, 0, 1, 1, None) == -1 and b"matrix batch" in lib.kb200_last_error()
+    assert warp(p8, p8, p8, p8, None, p8, 2, 3, 8, 8, 8, 8, 2, 1, 0, 3, 1, 1, None) == -1 and b"fill vector" in lib.kb200_last_error()
+    assert warp(p8, p8, p8, p8, None, p8, 2, 3, 8, 8, 8, 8, 2, 1, 0, 0, 1, 3, None) == -1 and b"normalize" in lib.kb200_last_error()
+    assert warp(p8, p8, p8, p8, None, p8, 2, 3, 8, 8, 8, 8, 2, 1, 5, 0, 1, 1, None) == -1 and b"bad interp" in lib.kb200_last_error()
+    assert warp(p8, p8, p8, p8, None, p8, 2, 3, 8, 8, 8, 8, 2, 1, 0, 7, 1, 1, None) == -1 and b"bad pad" in lib.kb200_last_error()
+    und = lib.kb200_undistort_u8hwc_forward
+    assert und(p8, None, p8, 2, 3, 8, 8, 1, None) == -1
+    assert und(p8, p8, p8, 2, 3, 8, 8, 9, None) == -1 and b"normalize" in lib.kb200_last_error()
+    assert und(p8, p8, p8, 2, 2, 8, 8, 1, None) == -3       # two channels: the host converts and takes the fp32 path
+    assert und(p8, p8, p8, 2, 3, 8, 7, 1, None) == -3       # odd width
+    assert und(ctypes.c_void_p(9), p8, p8, 2, 3, 8, 8, 1, None) == -3 and b"4-byte aligned" in lib.kb200_last_error()

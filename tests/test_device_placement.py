@@ -14,7 +14,7 @@ from kornia_b200 import _lib, _ops
 from conftest import golden
 from helpers import family_grads, run_family_case
 
-CASES = [(g, n) for g in ("family", "wider") for n in golden(g).names()]
+CASES = [(g, n) for g in ("family", "wider", "ingest") for n in golden(g).names()]
 # host logic that reads a value back from the device (a crop size, the reference's own `.item()`): meta cannot answer;
 # these ran on hardware in round 1 (tests/test_family_gpu.py)
 READS_BACK = ("crop_", "center_crop")
