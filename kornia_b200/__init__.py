@@ -20,6 +20,12 @@ __version__ = "0.1.0"
 # (`KB200_OPTIN=all python -m pytest tests -m gpu`): the C library reads the switches with getenv at call time.
 OPTIN_SWITCHES = ("KB200_SEP_VWALK", "KB200_SSIM_VWALK", "KB200_TILED_GRADIENT", "KB200_BWD_V2", "KB200_REMAP_V2", "KB200_FUSED_UNDISTORT",
                   "KB200_FUSED_PYRDOWN", "KB200_FAST_FILTER_BWD")
+# Switches promoted to defaults: a kernel that has passed its bit-identity tests on hardware and measured faster is turned on
+# by adding its switch here (one line, no C change: every switch is read with getenv at call time); NAME=0 in the environment
+# still selects the kernel it replaced.  Empty until the first GPU call of round 2 (tools/r2_first_call.sh) has reported.
+DEFAULT_ON: tuple = ()
+for _name in DEFAULT_ON:
+    __import__("os").environ.setdefault(_name, "1")
 if __import__("os").environ.get("KB200_OPTIN") == "all":
     for _name in OPTIN_SWITCHES:
         __import__("os").environ.setdefault(_name, "1")
