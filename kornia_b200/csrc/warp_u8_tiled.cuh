@@ -1,4 +1,4 @@
-// kornia_b200 -- tiled uint8 ingest warp (fp32 out, bilinear, zeros / border / reflection, C in {1,3}).
+// kornia_b200 -- tiled uint8 ingest warp (fp32 out, bilinear, zeros / border / reflection / fill, C in {1,3}).
 //
 // warp_fwd_u8hwc (warp_u8.cuh) converts every tap where it is gathered: 4 taps x C conversions per output pixel, each
 // behind its own byte load.  Here one CTA owns a 64 x 32 output tile, in the structure of remap_tiled_kernel
@@ -30,13 +30,13 @@ namespace kb200 {
 // identity maps never take.
 template <int NC, int PAD, bool ALIGN>
 __device__ __noinline__ void u8_exact_pixel(const unsigned char* img, int H, int W, float ux, float uy, float scale, bool divide, float* o,
-                                            size_t oplane) {
+                                            size_t oplane, const float* fill) {
   PixelSampler<float, KB200_BILINEAR, PAD> S;
   S.prepare(ux, uy, H, W, ALIGN);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const float v = S.sample_with([&](int off) { return value_of_byte(__ldg(img + (size_t)off * NC + c), scale, divide); });
-    __stcs(o + c * oplane, v);
+    __stcs(o + c * oplane, S.finish(v, PAD == KB200_FILL ? ldg(fill + c) : 0.0f));
   }
 }
 
@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(256, KIND == U8_KIND_LENS ? 3 : 4) warp_u8_til
   constexpr int NJ = 2, RPW = 4;
   constexpr int PLANE = BW * BH;
   static_assert(BW % 4 == 0, "whole 4-pixel groups per window row");
-  constexpr bool INTERIOR = PAD == KB200_REFLECTION;
+  // reflection and fill: the window is clipped to pixels whose whole footprint is inside the image -- there the reflection
+  // is the identity and the coverage of 'fill' (imgwarp.py:308-320: sample + (1 - sum of in-image weights) * fill) is complete
+  constexpr bool INTERIOR = PAD == KB200_REFLECTION || PAD == KB200_FILL;
   constexpr bool PRECLAMP = PAD == KB200_BORDER;
 
   extern __shared__ __align__(128) unsigned char u8t_smem[];
@@ -85,6 +87,9 @@ __global__ void __launch_bounds__(256, KIND == U8_KIND_LENS ? 3 : 4) warp_u8_til
   const float nfx = R::div(2.f, fmaxf(Wm1, 1e-8f)), nfy = R::div(2.f, fmaxf(Hm1, 1e-8f));
   const float scale = p.normalize == 1 ? RCP_255 : 1.0f;
   const bool divide = p.normalize == 2;
+  float fillv[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) fillv[c] = PAD == KB200_FILL ? ldg(p.fill + c) : 0.0f;
 
   // ---- 1. coordinates of this thread's pixels
   float ux[RPW * NJ], uy[RPW * NJ];  // unnormalised, un-padded (what the exact path consumes)
@@ -238,10 +243,14 @@ __global__ void __launch_bounds__(256, KIND == U8_KIND_LENS ? 3 : 4) warp_u8_til
           a = R::fma(tma::lds(a0 + (c * PLANE + 1) * 4), w_ne, a);
           a = R::fma(tma::lds(a0 + (c * PLANE + BW) * 4), w_sw, a);
           a = R::fma(tma::lds(a0 + (c * PLANE + BW + 1) * 4), w_se, a);
+          if (PAD == KB200_FILL) {  // PixelSampler's coverage in tap order (all four taps in the image here), then finish()
+            const float cover = R::add(R::add(R::add(R::add(0.f, w_nw), w_ne), w_sw), w_se);
+            a = R::add(a, R::mul(R::sub(1.f, cover), fillv[c]));
+          }
           __stcs(o + c * oplane, a);
         }
       } else {
-        u8_exact_pixel<NC, PAD, ALIGN>(img, H, W, ux[u], uy[u], scale, divide, o, oplane);
+        u8_exact_pixel<NC, PAD, ALIGN>(img, H, W, ux[u], uy[u], scale, divide, o, oplane, p.fill);
       }
     }
   }

@@ -89,3 +89,5 @@ def test_property_tests(on_cpu):
     T.test_ingest_headline_homographies_match_the_fp32_path()
     T.test_undistort_from_bytes_full_size()
     T.test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(on_cpu, "reflection", 3)
+    T.test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(on_cpu, "fill", 3)
+    T.test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(on_cpu, "fill", 1)

@@ -90,7 +90,7 @@ def test_ingest_headline_homographies_match_the_fp32_path():
     assert torch.equal(got, want), float((got - want).abs().max())
 
 
-@pytest.mark.parametrize("pad", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("pad", ["zeros", "border", "reflection", "fill"])
 @pytest.mark.parametrize("channels", [1, 3])
 def test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(monkeypatch, pad, channels):
     """warp_u8_tiled_kernel (window staged in shared memory, each byte converted once) against warp_fwd_u8hwc (KB200_U8_SIMPLE=1):
@@ -104,19 +104,21 @@ def test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(monkeypatch,
     g = torch.Generator().manual_seed(3)
     M = bench.perspective_from_quads(quad, quad + 6.0 * torch.randn(B, 4, 2, generator=g)).to(DEV)
     wild = _wild_matrices(H, W).to(DEV)
-    for mats, size in ((M, (H, W)), (M, (201, 333)), (wild, (H, W))):
+    fill = {} if pad != "fill" else dict(fill_value=torch.tensor([0.2, 0.4, 0.6][:channels]))
+    cases = ((M, (H, W)), (M, (201, 333)), (wild, (H, W))) if not (pad == "fill" and channels != 3) else ()  # warp_perspective fills RGB only
+    for mats, size in cases:
         img = frames[: mats.shape[0]] if mats.shape[0] <= B else frames[:1].expand(mats.shape[0], H, W, channels).contiguous()
         for ac in (True, False):
             monkeypatch.setenv("KB200_U8_SIMPLE", "1")
-            want = KT.warp_perspective_from_uint8(img, mats, size, padding_mode=pad, align_corners=ac)
+            want = KT.warp_perspective_from_uint8(img, mats, size, padding_mode=pad, align_corners=ac, **fill)
             monkeypatch.delenv("KB200_U8_SIMPLE")
-            got = KT.warp_perspective_from_uint8(img, mats, size, padding_mode=pad, align_corners=ac)
+            got = KT.warp_perspective_from_uint8(img, mats, size, padding_mode=pad, align_corners=ac, **fill)
             assert torch.equal(got, want), float((got - want).abs().max())
     rot = KT.get_rotation_matrix2d(torch.tensor([[W / 2, H / 2]], device=DEV).expand(B, 2), torch.linspace(-40, 40, B, device=DEV), torch.ones(B, 2, device=DEV))
     monkeypatch.setenv("KB200_U8_SIMPLE", "1")
-    want = KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad)
+    want = KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad, **fill)
     monkeypatch.delenv("KB200_U8_SIMPLE")
-    assert torch.equal(KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad), want)
+    assert torch.equal(KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad, **fill), want)
 
 
 @pytest.mark.parametrize("name", UNDISTORT)
