@@ -55,6 +55,7 @@ for shape in ((3, 100, 192, 3), (2, 33, 45, 3), (2, 70, 132, 1), (1, 5, 4, 3)):
     os.environ.pop("KB200_U8_SIMPLE")
     if shape[3] == 3:
         KT.warp_perspective_from_uint8(frames, Mq, (shape[1], shape[2]), mode="bicubic", padding_mode="fill", fill_value=torch.tensor([0.1, 0.2, 0.3]))
+        KT.warp_perspective_from_uint8(frames, Mq, (shape[1], shape[2]), padding_mode="fill", fill_value=torch.tensor([0.1, 0.2, 0.3]))
 for shape in ((3, 100, 192, 3), (2, 70, 132, 1), (1, 33, 45, 3)):  # the last one: odd width -> conversion + fp32 path
     frames = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).to(dev)
     camq = torch.tensor([[0.8 * shape[2], 0.0, shape[2] / 2], [0.0, 0.8 * shape[2], shape[1] / 2], [0.0, 0.0, 1.0]], device=dev).expand(shape[0], 3, 3).contiguous()
