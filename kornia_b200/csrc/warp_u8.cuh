@@ -49,7 +49,9 @@ __device__ __forceinline__ float unit_from_byte(unsigned char u) { return unit_f
 __device__ __forceinline__ float value_of_level(float x, float scale, bool divide) {
   return divide ? unit_from_level(x) : __fmul_rn(x, scale);
 }
-__device__ __forceinline__ float value_of_byte(unsigned char u, float scale, bool divide) { return value_of_level((float)u, scale, divide); }
+// float(byte) as 2^23 + byte with the 2^23 removed (one LOP3 + one FADD, both exact) rather than through the conversion pipe
+__device__ __forceinline__ float level_of_byte(unsigned char u) { return __fadd_rn(__uint_as_float(0x4B000000u | (unsigned)u), -8388608.0f); }
+__device__ __forceinline__ float value_of_byte(unsigned char u, float scale, bool divide) { return value_of_level(level_of_byte(u), scale, divide); }
 
 // float(byte q of word) without the conversion pipe: one PRMT drops the byte into the mantissa of 2^23 (0x4B0000bb =
 // 2^23 + bb exactly), one FADD removes the 2^23 -- both exact, so the result is the I2F's.

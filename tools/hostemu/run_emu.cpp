@@ -641,6 +641,7 @@ static void test_u8_undistort(int B, int H, int W, int normalize, bool strong) {
 static void test_u8_all() {
   int bad = 0;
   for (int v = 0; v < 256; ++v) bad += unit_from_byte((unsigned char)v) != (float)v / 255.0f;
+  for (int v = 0; v < 256; ++v) bad += level_of_byte((unsigned char)v) != (float)v;
   for (int v = 0; v < 256; ++v)  // the PRMT + FADD conversion of the tiled loader, every byte in every lane of a word
     for (int q = 0; q < 4; ++q) bad += level_of_word_byte(0xA5C3E17Bu ^ (((unsigned)v ^ ((0xA5C3E17Bu >> (8 * q)) & 255u)) << (8 * q)), q) != (float)v;
   if (bad) {
