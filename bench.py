@@ -276,6 +276,17 @@ def e2e_run(K, M_dev, B, steps, warmup, chunk, dev):
     return ms, f"pinned host buffers ({host}), chunk={chunk} samples, 3 streams (H2D / kernel / D2H), {n_el * 4} B each way per step"
 
 
+def max_over_ranks_or_none(dist, ms, note, device):
+    """Max over ranks of a per-rank time that some ranks may not have (None, e.g. a pinned allocation that failed): EVERY rank
+    takes part in the one all_reduce -- a missing value travels as +inf -- and all ranks return the same (ms | None, note)."""
+    t = torch.tensor([ms if ms is not None else float("inf")], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    worst = float(t.item())
+    if math.isfinite(worst):
+        return worst, note
+    return None, note if ms is None else "unavailable on another rank"
+
+
 def run_ours(args) -> None:
     import kornia_b200 as K
     from kornia_b200 import _lib, _ops
@@ -338,12 +349,7 @@ def run_ours(args) -> None:
     # ---------------------------------------------------------------- e2e (host buffers)
     e2e_ms, e2e_note = e2e_run(K, M, B, steps=max(2, min(args.steps, 3)), warmup=1, chunk=args.e2e_chunk, dev=dev)
     if dist is not None:
-        # every rank takes part, also one whose pinned allocation failed (it contributes +inf): no rank may skip a collective
-        t = torch.tensor([e2e_ms if e2e_ms is not None else float("inf")], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if e2e_ms is not None and not math.isfinite(float(t.item())):
-            e2e_note = "pinned allocation failed on another rank"
-        e2e_ms = float(t.item()) if math.isfinite(float(t.item())) else None
+        e2e_ms, e2e_note = max_over_ranks_or_none(dist, e2e_ms, e2e_note, dev)
     barrier()
     if rank != 0:
         if dist is not None:

@@ -56,6 +56,12 @@ def _worker(rank, world, port, B, q):
         t = torch.tensor([float(rank + 1)])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         assert t.item() == world
+        # bench.py's e2e reduction: a rank without a value (its pinned allocation failed) still joins the collective
+        import bench
+
+        assert bench.max_over_ranks_or_none(dist, 10.0 + rank, "ok", "cpu") == (10.0 + world - 1, "ok")
+        got = bench.max_over_ranks_or_none(dist, None if rank == 1 else 5.0, "failed here" if rank == 1 else "ok", "cpu")
+        assert got == (None, "failed here" if rank == 1 else "unavailable on another rank")
     finally:
         dist.destroy_process_group()
 
