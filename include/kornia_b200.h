@@ -120,7 +120,7 @@ int kb200_undistort_forward(const void* src, const void* lens, void* out, int B,
  * out (B,C,h,w) fp32.  normalize: 0 keeps float(byte); 1 multiplies by the fp32 reciprocal of 255, which is how torch's
  * CUDA backend evaluates `image.float() / 255.0` (so the result is bit-identical to the reference's three steps on this
  * device); 2 divides, as torch's CPU backend does (one ulp apart for 126 of the 256 byte values).  Forward only (a uint8 image has no gradient).
- * Bilinear (any of the four paddings), C in {1,3}, W % 4 == 0 and a 4-byte aligned src run the
+ * Bilinear (any of the four paddings), C in {1,3,4}, W % 4 == 0 and a 4-byte aligned src run the
  * shared-memory tiled kernel (warp_u8_tiled.cuh); everything else, or KB200_U8_SIMPLE=1, the per-tap kernel (warp_u8.cuh);
  * the two agree bit for bit.
  * Status: written after the round-1 GPU budget was spent -- compiled for sm_100a, executed on the host emulator, not yet

@@ -49,7 +49,7 @@ static int launch_u8_tiled(const WarpU8Params& p, cudaStream_t st) {
 static int u8_tiled_forward(const WarpU8Params& p, int projective, int interp, int pad, cudaStream_t st) {
   const char* simple = getenv("KB200_U8_SIMPLE");
   if (simple && simple[0] == '1') return KB200_EUNSUPPORTED;
-  if (interp != KB200_BILINEAR || (p.C != 1 && p.C != 3)) return KB200_EUNSUPPORTED;
+  if (interp != KB200_BILINEAR || (p.C != 1 && p.C != 3 && p.C != 4)) return KB200_EUNSUPPORTED;
   // aligned 32-bit loads of whole in-image groups of 4 pixels: every image row starts on a 4-byte boundary
   if (p.W % 4 != 0 || (reinterpret_cast<uintptr_t>(p.src) & 3) != 0) return KB200_EUNSUPPORTED;
   if (p.B > 65535 || ceil_div(p.h, 32) > 65535) return KB200_EUNSUPPORTED;
@@ -66,6 +66,10 @@ static int u8_tiled_forward(const WarpU8Params& p, int projective, int interp, i
   KB_U8T_CASE(1, KB200_REFLECTION)
   KB_U8T_CASE(3, KB200_FILL)
   KB_U8T_CASE(1, KB200_FILL)
+  KB_U8T_CASE(4, KB200_ZEROS)  // RGBA / BGRA frames
+  KB_U8T_CASE(4, KB200_BORDER)
+  KB_U8T_CASE(4, KB200_REFLECTION)
+  KB_U8T_CASE(4, KB200_FILL)
 #undef KB_U8T_CASE
   return KB200_EUNSUPPORTED;
 }

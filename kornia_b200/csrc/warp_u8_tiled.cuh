@@ -1,4 +1,4 @@
-// kornia_b200 -- tiled uint8 ingest warp (fp32 out, bilinear, zeros / border / reflection / fill, C in {1,3}).
+// kornia_b200 -- tiled uint8 ingest warp (fp32 out, bilinear, zeros / border / reflection / fill, C in {1,3,4}).
 //
 // warp_fwd_u8hwc (warp_u8.cuh) converts every tap where it is gathered: 4 taps x C conversions per output pixel, each
 // behind its own byte load.  Here one CTA owns a 64 x 32 output tile, in the structure of remap_tiled_kernel
@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(256, KIND == U8_KIND_LENS ? 3 : 4) warp_u8_til
   }
 }
 
+static_assert(4 * 72 * 40 * 4 + 32 * 4 + 4 * 4 + 3 * 4 + 4 <= 48 * 1024, "the RGBA box fits the default dynamic shared-memory limit");
 constexpr int U8T_SMEM_BYTES(int nc) { return nc * 72 * 40 * 4 + 32 * 4 + 4 * 4 + 3 * 4 + 4; }
 
 }  // namespace kb200

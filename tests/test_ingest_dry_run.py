@@ -91,3 +91,5 @@ def test_property_tests(on_cpu):
     T.test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(on_cpu, "reflection", 3)
     T.test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(on_cpu, "fill", 3)
     T.test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(on_cpu, "fill", 1)
+    T.test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(on_cpu, "border", 4)
+    T.test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(on_cpu, "fill", 4)

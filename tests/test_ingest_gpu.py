@@ -91,7 +91,7 @@ def test_ingest_headline_homographies_match_the_fp32_path():
 
 
 @pytest.mark.parametrize("pad", ["zeros", "border", "reflection", "fill"])
-@pytest.mark.parametrize("channels", [1, 3])
+@pytest.mark.parametrize("channels", [1, 3, 4])
 def test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(monkeypatch, pad, channels):
     """warp_u8_tiled_kernel (window staged in shared memory, each byte converted once) against warp_fwd_u8hwc (KB200_U8_SIMPLE=1):
     headline-like homographies, rotations that push tiles to the exact path, a horizon inside the image, partial tiles."""
@@ -104,7 +104,7 @@ def test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(monkeypatch,
     g = torch.Generator().manual_seed(3)
     M = bench.perspective_from_quads(quad, quad + 6.0 * torch.randn(B, 4, 2, generator=g)).to(DEV)
     wild = _wild_matrices(H, W).to(DEV)
-    fill = {} if pad != "fill" else dict(fill_value=torch.tensor([0.2, 0.4, 0.6][:channels]))
+    fill = {} if pad != "fill" else dict(fill_value=torch.tensor([0.2, 0.4, 0.6, 0.8][:channels]))
     cases = ((M, (H, W)), (M, (201, 333)), (wild, (H, W))) if not (pad == "fill" and channels != 3) else ()  # warp_perspective fills RGB only
     for mats, size in cases:
         img = frames[: mats.shape[0]] if mats.shape[0] <= B else frames[:1].expand(mats.shape[0], H, W, channels).contiguous()

@@ -580,7 +580,7 @@ static void test_u8_tiled(int B, int H, int W, int h, int w, int normalize, bool
     memcpy(&m[(size_t)b * 9], M, sizeof(M));
   }
   WarpU8Params u{};
-  static const float fillc[3] = {0.25f, 0.5f, 0.75f};
+  static const float fillc[4] = {0.25f, 0.5f, 0.75f, 1.0f};
   u.src = bytes; u.m = m.data(); u.bx = bx.data(); u.by = by.data(); u.fill = fillc;
   u.B = B; u.C = NC; u.H = H; u.W = W; u.h = h; u.w = w; u.Bm = shared_m ? 1 : B; u.align = ALIGN; u.normalize = normalize;
   u.out = o2.data();
@@ -671,6 +671,9 @@ static void test_u8_all() {
   test_u8_tiled<3, KB200_FILL, true, true>(3, 70, 132, 70, 132, 1, true, false);
   test_u8_tiled<3, KB200_FILL, true, false>(2, 40, 76, 66, 130, 2, false, false);
   test_u8_tiled<1, KB200_FILL, false, true>(2, 33, 64, 40, 70, 0, true, true);
+  test_u8_tiled<4, KB200_ZEROS, true, true>(2, 70, 132, 70, 132, 1, true, false);
+  test_u8_tiled<4, KB200_FILL, false, false>(2, 33, 64, 40, 70, 2, false, false);
+  test_u8_tiled<4, KB200_REFLECTION, true, true>(1, 40, 76, 66, 130, 0, true, false);
   test_u8_undistort<3>(2, 70, 132, 1, false);
   test_u8_undistort<3>(2, 97, 200, 2, true);
   test_u8_undistort<1>(1, 33, 64, 0, false);
@@ -682,7 +685,7 @@ static void fuzz(int rounds) {
   for (int r = 0; r < rounds; ++r) {
     const int H = pick(1, 110), W = 4 * pick(1, 70), planes = pick(1, 4), lazy = pick(0, 1);
     const unsigned grid = (unsigned)pick(1, 9);
-    switch (pick(0, 23)) {
+    switch (pick(0, 24)) {
       case 10: if (H > 1 && W > 1) test_filter2d<3, KB200_REFLECT>(planes, H, W, grid, lazy); break;
       case 11: if (H > 3 && W > 3) test_filter2d<7, KB200_REPLICATE>(planes, H, W, grid, lazy); break;
       case 12: test_filter2d<7, KB200_CONSTANT>(planes, H, W, grid, lazy); break;
@@ -696,6 +699,7 @@ static void fuzz(int rounds) {
       case 20: test_u8_tiled<1, KB200_REFLECTION, true, false>(pick(1, 3), H, W, H, W, pick(0, 2), pick(0, 1), false, false); break;
       case 21: test_u8_tiled<3, KB200_REFLECTION, true, true>(pick(1, 2), H, W, std::max(1, H - pick(0, 5)), W, pick(0, 2), pick(0, 1), false, false); break;
       case 23: test_u8_tiled<3, KB200_FILL, true, true>(pick(1, 2), H, W, std::max(1, H - pick(0, 5)), std::max(1, W - pick(0, 9)), pick(0, 2), pick(0, 1), false, false); break;
+      case 24: test_u8_tiled<4, KB200_BORDER, true, false>(pick(1, 2), H, W, std::max(1, H - pick(0, 5)), std::max(1, W - pick(0, 9)), pick(0, 2), pick(0, 1), false, false); break;
       case 22: if (H > 1) test_u8_undistort<3>(pick(1, 2), H, W, pick(0, 2), pick(0, 1)); break;
       case 0: if (H > 5 && W > 5) test_sepfilter<11, KB200_REFLECT>(1, planes, H, W, grid, lazy); break;
       case 1: if (H > 8 && W > 8) test_sepfilter<17, KB200_REPLICATE>(1, planes, H, W, grid, lazy); break;

@@ -44,7 +44,7 @@ KT.resize(src, (40, 77), antialias=True)
 cam = torch.tensor([[150.0, 0.0, 96.0], [0.0, 150.0, 50.0], [0.0, 0.0, 1.0]], device=dev).expand(B, 3, 3).contiguous()
 KC.undistort_image(src, cam, torch.tensor([[-0.2, 0.05, 0.001, -0.002, 0.01]], device=dev).expand(B, 5).contiguous())
 # uint8 ingest warps: the tiled kernel (W % 4 == 0), the per-tap kernel (odd width; KB200_U8_SIMPLE=1), partial tiles, every padding
-for shape in ((3, 100, 192, 3), (2, 33, 45, 3), (2, 70, 132, 1), (1, 5, 4, 3)):
+for shape in ((3, 100, 192, 3), (2, 33, 45, 3), (2, 70, 132, 1), (1, 5, 4, 3), (2, 40, 64, 4)):
     frames = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).to(dev)
     Mq = M[: shape[0]].clone()
     for simple in ("0", "1"):
