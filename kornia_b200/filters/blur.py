@@ -11,7 +11,6 @@ from .kernels import _unpack_2d_ks, get_box_kernel1d, get_box_kernel2d
 __all__ = ["box_blur", "BoxBlur"]
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def box_blur(input: torch.Tensor, kernel_size: tuple[int, int] | int, border_type: str = "reflect",
              separable: bool = False) -> torch.Tensor:
     """Mean filter over a ``kernel_size`` window of every channel of ``input`` (B,C,H,W).

@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from .._ops import Filter2dFunction, SepFilterFunction
+from .. import _ops
 from ..core.check import check, check_is_tensor, check_shape
 from .kernels import normalize_kernel2d
 
@@ -46,7 +46,6 @@ def _border_code(border_type: str, x: torch.Tensor, kh: int, kw: int, same: bool
     return code
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def filter2d(
     input: torch.Tensor,
     kernel: torch.Tensor,
@@ -77,10 +76,9 @@ def filter2d(
         taps = normalize_kernel2d(taps)
     same = padding == "same"
     kh, kw = taps.shape[-2:]
-    return Filter2dFunction.apply(input, taps, _border_code(border_type, input, kh, kw, same), same)
+    return _ops.filter2d(input, taps, _border_code(border_type, input, kh, kw, same), same)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def filter2d_separable(
     input: torch.Tensor,
     kernel_x: torch.Tensor,
@@ -109,4 +107,4 @@ def filter2d_separable(
         ky = normalize_kernel2d(ky[:, :, None])[:, :, 0]
     same = padding == "same"
     code = _border_code(border_type, input, ky.shape[-1], kx.shape[-1], same)
-    return SepFilterFunction.apply(input, kx, ky, code, same)
+    return _ops.sepfilter(input, kx, ky, code, same)

@@ -12,7 +12,6 @@ from .kernels import _check_kernel_size, _unpack_2d_ks, get_gaussian_kernel1d, g
 __all__ = ["gaussian_blur2d", "GaussianBlur2d"]
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def gaussian_blur2d(
     input: torch.Tensor,
     kernel_size: tuple[int, int] | int,
@@ -73,13 +72,18 @@ _TAPS_CACHE: dict = {}
 
 
 def _constant_taps(kernel_size, sigma_key, separable, device, dtype):
+    """Taps of constant sigmas, cached per (size, sigma, device, dtype).  Built outside the caller's inference-mode / grad
+    scope so that a tensor cached during an eval pass can still be saved for a later backward; rebuilt in-graph under
+    ``torch.compile`` tracing (no global state there)."""
+    if torch.compiler.is_compiling():
+        return _taps(kernel_size, torch.tensor([sigma_key], device=device, dtype=dtype), separable)
     ks = kernel_size if isinstance(kernel_size, int) else tuple(kernel_size)
     key = (ks, sigma_key, bool(separable), str(device), dtype)
     hit = _TAPS_CACHE.get(key)
     if hit is None:
         if len(_TAPS_CACHE) >= 256:
             _TAPS_CACHE.clear()
-        with torch.no_grad():
+        with torch.inference_mode(False), torch.no_grad():
             hit = _TAPS_CACHE[key] = _taps(kernel_size, torch.tensor([sigma_key], device=device, dtype=dtype), separable)
     return hit
 

@@ -10,7 +10,6 @@ from .kernels import get_laplacian_kernel2d, normalize_kernel2d
 __all__ = ["laplacian", "Laplacian"]
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def laplacian(input: torch.Tensor, kernel_size: tuple[int, int] | int, border_type: str = "reflect",
               normalized: bool = True) -> torch.Tensor:
     """Filter every channel of ``input`` (B,C,H,W) with the ones-and-centre Laplacian kernel;

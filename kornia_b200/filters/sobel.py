@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .._ops import SpatialGradientFunction
+from .. import _ops
 from ..core.check import check_is_tensor, check_shape
 from .kernels import get_spatial_gradient_kernel2d, normalize_kernel2d
 
@@ -19,20 +19,24 @@ __all__ = ["spatial_gradient", "sobel", "SpatialGradient", "Sobel"]
 _TAPS: dict = {}
 
 
+@torch.compiler.assume_constant_result
 def _host_taps(mode: str, order: int, normalized: bool, dtype: torch.dtype):
     """Derivative taps as python floats, built (and normalised) with the reference's torch ops in
-    ``dtype`` so that they carry exactly the values the reference convolves with."""
+    ``dtype`` so that they carry exactly the values the reference convolves with.  Constants of the call: evaluated with
+    real tensors even while a tracer (dynamo, torch.export) runs the caller under fake tensors."""
     key = (mode, order, bool(normalized), dtype)
     hit = _TAPS.get(key)
     if hit is None:
-        kernel = get_spatial_gradient_kernel2d(mode, order, dtype=dtype)
-        if normalized:
-            kernel = normalize_kernel2d(kernel)
-        hit = _TAPS[key] = (tuple(kernel.double().flatten().tolist()), kernel.shape[0], kernel.shape[-1])
+        from torch._subclasses.fake_tensor import unset_fake_temporarily
+
+        with unset_fake_temporarily(), torch.inference_mode(False), torch.no_grad():
+            kernel = get_spatial_gradient_kernel2d(mode, order, dtype=dtype)
+            if normalized:
+                kernel = normalize_kernel2d(kernel)
+            hit = _TAPS[key] = (tuple(kernel.double().flatten().tolist()), kernel.shape[0], kernel.shape[-1])
     return hit
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def spatial_gradient(input: torch.Tensor, mode: str = "sobel", order: int = 1, normalized: bool = True) -> torch.Tensor:
     """Image derivatives of every channel of ``input`` (B,C,H,W) over a replicate border:
     (B,C,2,H,W) = (d/dx, d/dy) for ``order=1``, (B,C,3,H,W) = (dxx, dxy, dyy) for ``order=2``;
@@ -40,20 +44,19 @@ def spatial_gradient(input: torch.Tensor, mode: str = "sobel", order: int = 1, n
     check_is_tensor(input)
     check_shape(input, ["B", "C", "H", "W"])
     taps, nout, k = _host_taps(mode, order, normalized, input.dtype)
-    return SpatialGradientFunction.apply(input, taps, nout, k, False, 0.0)
+    return _ops.spatial_gradient(input, taps, nout, k, False, 0.0)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def sobel(input: torch.Tensor, normalized: bool = True, eps: float = 1e-6) -> torch.Tensor:
     """Sobel edge magnitude ``sqrt(gx^2 + gy^2 + eps)`` of every channel of ``input`` (B,C,H,W)."""
     check_is_tensor(input)
     check_shape(input, ["B", "C", "H", "W"])
     taps, nout, k = _host_taps("sobel", 1, normalized, input.dtype)
     if torch.is_grad_enabled() and input.requires_grad:
-        edges = SpatialGradientFunction.apply(input, taps, nout, k, False, 0.0)
+        edges = _ops.spatial_gradient(input, taps, nout, k, False, 0.0)
         gx, gy = edges[:, :, 0], edges[:, :, 1]
         return torch.sqrt(gx * gx + gy * gy + eps)
-    return SpatialGradientFunction.apply(input, taps, nout, k, True, eps)
+    return _ops.spatial_gradient(input, taps, nout, k, True, eps)
 
 
 class SpatialGradient(nn.Module):

@@ -9,7 +9,6 @@ from .gaussian import gaussian_blur2d
 __all__ = ["unsharp_mask", "UnsharpMask"]
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def unsharp_mask(input: torch.Tensor, kernel_size: tuple[int, int] | int, sigma: tuple[float, float] | torch.Tensor,
                  border_type: str = "reflect") -> torch.Tensor:
     """Sharpen: ``2 * input - gaussian_blur2d(input)``, evaluated as the reference's ``lerp(blur, input, 2)`` so
@@ -65,17 +64,10 @@ def _fused_unsharp(input, kernel_size, sigma, border_type):
     if req is None:
         return None
     kx, ky, code = req
-    B, C, H, W = input.shape
-    x = input.contiguous()
-    out = torch.empty_like(x)
     try:
-        with torch.cuda.device(x.device), _ops._Timed("sepfilter_lerp_forward", x):
-            _lib.call("kb200_sepfilter_lerp_forward", x.data_ptr(), kx.data_ptr(), ky.data_ptr(), out.data_ptr(), B, C, H, W, kx.shape[0],
-                      kx.shape[1], ky.shape[0], ky.shape[1], code, 1, 2.0, _lib.F32, _ops._stream(x))
+        return _ops.ops.sepfilter_lerp_fwd(input, kx, ky, code, 2.0)
     except _lib.Unsupported:
         return None
-    _ops._bump()
-    return out
 
 
 class UnsharpMask(nn.Module):

@@ -53,11 +53,17 @@ _AXES_CACHE_MAX = 64
 
 
 def _cached(key, build):
+    """Process-wide cache of small constant tensors.  Entries are built outside any inference-mode / grad scope of the
+    caller: a tensor created under ``torch.inference_mode()`` could not be saved for a later backward (the reference
+    has no such state to trip over).  Under ``torch.compile`` tracing the tensors are rebuilt in-graph (no global state)."""
+    if torch.compiler.is_compiling():
+        return build()
     hit = _AXES_CACHE.get(key)
     if hit is None:
         if len(_AXES_CACHE) >= _AXES_CACHE_MAX:
             _AXES_CACHE.clear()
-        hit = _AXES_CACHE[key] = build()
+        with torch.inference_mode(False), torch.no_grad():
+            hit = _AXES_CACHE[key] = build()
     return hit
 
 
@@ -86,55 +92,26 @@ def affine_axes(h: int, w: int, align_corners: bool, device, dtype):
 
 
 # ---------------------------------------------------------------------------------------------
-# one-launch prelude (kb200_warp_prelude) for the common no-grad-on-M case
+# one-launch prelude (torch.ops.kornia_b200.warp_prelude, autograd formula = warp_prelude_bwd)
 # ---------------------------------------------------------------------------------------------
-FUSED_VARIANT = 4       # the contraction orders that reproduce torch's CUDA kernels bit for bit (GPU-tested)
 FUSED_MIN_BATCH = 2     # below this torch's bmm takes a different (gemv-like) path; keep the torch ops there
 
 
-class _FusedPrelude(torch.autograd.Function):
-    """kb200_warp_prelude forward (bit-identical to the torch op sequence) + its one-launch backward."""
+def torch_prelude_forced() -> bool:
+    import os
 
-    @staticmethod
-    def forward(ctx, M, src_hw, dst_hw, affine):
-        from .. import _lib, _ops
-
-        Mc = M.contiguous()
-        out = torch.empty((Mc.shape[0], 3, 3), device=M.device, dtype=M.dtype)
-        dt = 0 if M.dtype == torch.float32 else 1
-        with torch.cuda.device(M.device):
-            _lib.call("kb200_warp_prelude", Mc.data_ptr(), out.data_ptr(), Mc.shape[0], 2 if affine else 3, int(src_hw[0]), int(src_hw[1]),
-                      int(dst_hw[0]), int(dst_hw[1]), dt, FUSED_VARIANT, torch.cuda.current_stream(M.device).cuda_stream)
-        _ops._bump()
-        ctx.save_for_backward(out)
-        ctx.cfg = (tuple(int(v) for v in src_hw), tuple(int(v) for v in dst_hw), bool(affine), dt)
-        return out
-
-    @staticmethod
-    def backward(ctx, gm):
-        from .. import _lib, _ops
-
-        (m,) = ctx.saved_tensors
-        src_hw, dst_hw, affine, dt = ctx.cfg
-        rows = 2 if affine else 3
-        gm = gm.contiguous()
-        gM = torch.empty((m.shape[0], rows, 3), device=m.device, dtype=m.dtype)
-        with torch.cuda.device(m.device):
-            _lib.call("kb200_warp_prelude_backward", m.data_ptr(), gm.data_ptr(), gM.data_ptr(), m.shape[0], rows, src_hw[0], src_hw[1],
-                      dst_hw[0], dst_hw[1], dt, torch.cuda.current_stream(m.device).cuda_stream)
-        _ops._bump()
-        return gM, None, None, None
+    return os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") == "1"
 
 
 def sampling_matrix(M: torch.Tensor, src_hw, dst_hw, affine: bool) -> torch.Tensor:
     """inverse(normalize_homography(M3)) -- the (B,3,3) dst-normalised -> src-normalised map the kernels
     consume.  One CUDA launch (and one more for its backward) when M is a CUDA fp32/fp64 tensor with batch >= 2;
-    the reference's torch op sequence otherwise, under double backward, or when KORNIA_B200_TORCH_PRELUDE=1."""
-    import os
+    the reference's torch op sequence otherwise or when KORNIA_B200_TORCH_PRELUDE=1.  The fused backward has no
+    autograd formula of its own: double backward through M needs KORNIA_B200_TORCH_PRELUDE=1."""
+    from .. import _ops
 
-    fused_ok = (M.is_cuda and M.dtype in (torch.float32, torch.float64) and M.shape[0] >= FUSED_MIN_BATCH
-                and os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") != "1")
+    fused_ok = (M.is_cuda and M.dtype in (torch.float32, torch.float64) and M.shape[0] >= FUSED_MIN_BATCH and not torch_prelude_forced())
     if not fused_ok:
         M3 = affine_to_homography(M) if affine else M
         return inverse3x3(normalize_homography(M3, src_hw, dst_hw))
-    return _FusedPrelude.apply(M, src_hw, dst_hw, affine)
+    return _ops.ops.warp_prelude(M, int(src_hw[0]), int(src_hw[1]), int(dst_hw[0]), int(dst_hw[1]), bool(affine))

@@ -47,7 +47,6 @@ def pack_lens(K: torch.Tensor, dist: torch.Tensor, like: torch.Tensor):
     return torch.cat([intrinsics.expand(n, 4), d[:, :12].expand(n, 12)], -1).contiguous()
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def undistort_image(image: torch.Tensor, K: torch.Tensor, dist: torch.Tensor) -> torch.Tensor:
     """Remove the lens distortion ``dist`` (*,4|5|8|12|14) of camera ``K`` (*,3,3) from ``image`` (*,C,H,W)."""
     if image.dim() < 3:
@@ -84,7 +83,6 @@ def undistort_image(image: torch.Tensor, K: torch.Tensor, dist: torch.Tensor) ->
     return out.view_as(image)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def undistort_image_from_uint8(image: torch.Tensor, K: torch.Tensor, dist: torch.Tensor, normalize=True) -> torch.Tensor:
     """``undistort_image(image_to_tensor(image).float() / 255, K, dist)`` for a decoder's uint8 ``image`` (B,H,W,C) or
     (H,W,C) -> fp32 (B,C,H,W) (the wire format and the maps fused).  One kernel

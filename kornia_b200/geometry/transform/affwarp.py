@@ -32,7 +32,6 @@ def _eye3(like: torch.Tensor) -> torch.Tensor:
     return torch.eye(3, device=like.device, dtype=like.dtype)[None].repeat(like.shape[0], 1, 1)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def affine(tensor: torch.Tensor, matrix: torch.Tensor, mode: str = "bilinear", padding_mode: str = "zeros",
            align_corners: bool = True) -> torch.Tensor:
     """Warp ``tensor`` ((C,H,W) or (B,C,H,W)) with the source->destination pixel matrices ``matrix``
@@ -54,7 +53,6 @@ def _check_image(tensor, other, other_name: str) -> None:
         raise TypeError(f"Input {other_name} type is not a torch.Tensor. Got {type(other)}")
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def rotate(tensor: torch.Tensor, angle: torch.Tensor, center: Optional[torch.Tensor] = None, mode: str = "bilinear",
            padding_mode: str = "zeros", align_corners: bool = True) -> torch.Tensor:
     """Rotate counter-clockwise (as displayed) by ``angle`` (B,) degrees about ``center`` (B,2; x,y),
@@ -72,7 +70,6 @@ def rotate(tensor: torch.Tensor, angle: torch.Tensor, center: Optional[torch.Ten
     return affine(tensor, matrix[..., :2, :3], mode, padding_mode, align_corners)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def translate(tensor: torch.Tensor, translation: torch.Tensor, mode: str = "bilinear", padding_mode: str = "zeros",
               align_corners: bool = True) -> torch.Tensor:
     """Shift by ``translation`` (B,2) = (dx, dy) pixels."""
@@ -86,7 +83,6 @@ def translate(tensor: torch.Tensor, translation: torch.Tensor, mode: str = "bili
     return affine(tensor, matrix[..., :2, :3], mode, padding_mode, align_corners)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def scale(tensor: torch.Tensor, scale_factor: torch.Tensor, center: Optional[torch.Tensor] = None, mode: str = "bilinear",
           padding_mode: str = "zeros", align_corners: bool = True) -> torch.Tensor:
     """Zoom by ``scale_factor`` ((B,) isotropic or (B,2) = (sx, sy)) about ``center`` (default: image centre)."""
@@ -102,7 +98,6 @@ def scale(tensor: torch.Tensor, scale_factor: torch.Tensor, center: Optional[tor
     return affine(tensor, matrix[..., :2, :3], mode, padding_mode, align_corners)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def shear(tensor: torch.Tensor, shear: torch.Tensor, mode: str = "bilinear", padding_mode: str = "zeros",
           align_corners: bool = False) -> torch.Tensor:
     """Skew by ``shear`` (B,2) = (shx, shy)."""
@@ -132,7 +127,6 @@ def _odd_at_least_3(sigma: float) -> int:
     return k if k % 2 else k + 1
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def resize(input: torch.Tensor, size: Union[int, Tuple[int, int]], interpolation: str = "bilinear",
            align_corners: Optional[bool] = None, side: str = "short", antialias: bool = False) -> torch.Tensor:
     """Resample the last two axes of ``input`` ((H,W), (C,H,W), (B,C,H,W) or (*,C,H,W)) onto ``size`` = (h, w), or

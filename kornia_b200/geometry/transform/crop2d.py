@@ -24,7 +24,6 @@ def _dst_corners(dst_h: int, dst_w: int, n: int, like: torch.Tensor) -> torch.Te
     return pts.expand(n, -1, -1)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def crop_and_resize(input_tensor: torch.Tensor, boxes: torch.Tensor, size: Tuple[int, int], mode: str = "bilinear",
                     padding_mode: str = "zeros", align_corners: bool = True) -> torch.Tensor:
     """Cut the quadrilaterals ``boxes`` (B,4,2; clockwise from top-left, x,y) out of ``input_tensor``
@@ -41,7 +40,6 @@ def crop_and_resize(input_tensor: torch.Tensor, boxes: torch.Tensor, size: Tuple
                          align_corners)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def center_crop(input_tensor: torch.Tensor, size: Tuple[int, int], mode: str = "bilinear", padding_mode: str = "zeros",
                 align_corners: bool = True) -> torch.Tensor:
     """Crop the central ``size`` = (h, w) window of every image of ``input_tensor`` (B,C,H,W)."""
@@ -58,7 +56,6 @@ def center_crop(input_tensor: torch.Tensor, size: Tuple[int, int], mode: str = "
     return crop_by_boxes(input_tensor, src, _dst_corners(dst_h, dst_w, 1, input_tensor), mode, padding_mode, align_corners)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def crop_by_boxes(input_tensor: torch.Tensor, src_box: torch.Tensor, dst_box: torch.Tensor, mode: str = "bilinear",
                   padding_mode: str = "zeros", align_corners: bool = True, validate_boxes: bool = True) -> torch.Tensor:
     """Warp the ``src_box`` quadrilaterals onto the ``dst_box`` rectangles (both (B,4,2)); the
@@ -74,7 +71,6 @@ def crop_by_boxes(input_tensor: torch.Tensor, src_box: torch.Tensor, dst_box: to
                                  padding_mode=padding_mode, align_corners=align_corners)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def crop_by_transform_mat(input_tensor: torch.Tensor, transform: torch.Tensor, out_size: Tuple[int, int],
                           mode: str = "bilinear", padding_mode: str = "zeros", align_corners: bool = True) -> torch.Tensor:
     """Resample ``input_tensor`` (B,C,H,W) through ``transform`` ((B|1,2,3) affine or (B|1,3,3)

@@ -14,7 +14,7 @@ import torch
 
 from .. import _prelude as P
 from ... import _lib
-from ..._ops import RemapFunction, WarpFunction
+from ... import _ops
 from ...core.check import check_shape
 
 __all__ = ["warp_perspective", "warp_affine", "remap"]
@@ -30,7 +30,6 @@ def _mode_codes(mode: str, padding_mode: str, allow_fill: bool):
     return _lib.INTERP[mode], _lib.PADDING[padding_mode]
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def warp_perspective(
     src: torch.Tensor,
     M: torch.Tensor,
@@ -77,10 +76,9 @@ def warp_perspective(
             # the reference's (1,3,1,1) fill cannot broadcast against C != 3 channels
             raise RuntimeError(f"The size of tensor a ({C}) must match the size of tensor b (3) at non-singleton dimension 1")
         fill = fill_value
-    return WarpFunction.apply(src, m, bx, by, fill, h_out, w_out, True, interp, pad, bool(align_corners))
+    return _ops.warp(src, m, bx, by, fill, h_out, w_out, True, interp, pad, bool(align_corners))
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def warp_affine(
     src: torch.Tensor,
     M: torch.Tensor,
@@ -126,10 +124,9 @@ def warp_affine(
         elif fill.ndim != 1 or fill.numel() != C:
             raise RuntimeError(f"The size of tensor a ({C}) must match the size of tensor b ({fill.shape[-1] if fill.ndim else 1}) "
                                "at non-singleton dimension 1")
-    return WarpFunction.apply(src, m, bx, by, fill, h_out, w_out, False, interp, pad, bool(align_corners))
+    return _ops.warp(src, m, bx, by, fill, h_out, w_out, False, interp, pad, bool(align_corners))
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def remap(
     image: torch.Tensor,
     map_x: torch.Tensor,
@@ -159,4 +156,4 @@ def remap(
                            "non-singleton dimension 0")
     if align_corners is None:
         align_corners = False
-    return RemapFunction.apply(image, map_x, map_y, bool(normalized_coordinates), interp, pad, bool(align_corners))
+    return _ops.remap(image, map_x, map_y, bool(normalized_coordinates), interp, pad, bool(align_corners))

@@ -60,7 +60,6 @@ def _no_grad_matrix(M: torch.Tensor) -> None:
                            "image.permute(0, 3, 1, 2).float() / 255")
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def warp_perspective_from_uint8(
     image: torch.Tensor,
     M: torch.Tensor,
@@ -102,7 +101,6 @@ def warp_perspective_from_uint8(
     return _ops.warp_u8hwc(image, m, bx, by, fill, h_out, w_out, True, interp, pad, bool(align_corners), norm)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def warp_affine_from_uint8(
     image: torch.Tensor,
     M: torch.Tensor,

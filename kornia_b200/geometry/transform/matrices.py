@@ -44,19 +44,11 @@ def _fused_ok(*tensors: torch.Tensor) -> bool:
 
 
 def _fused_rotation(center: torch.Tensor, angle: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
-    from ... import _lib, _ops
-    from .._prelude import FUSED_VARIANT
+    from ... import _ops
 
-    c, a, s = center.contiguous(), angle.contiguous(), scale.contiguous()
-    out = torch.empty((c.shape[0], 2, 3), device=c.device, dtype=c.dtype)
-    with torch.cuda.device(c.device):
-        _lib.call("kb200_rotation_matrix2d", c.data_ptr(), a.data_ptr(), s.data_ptr(), out.data_ptr(), c.shape[0],
-                  0 if c.dtype == torch.float32 else 1, FUSED_VARIANT, torch.cuda.current_stream(c.device).cuda_stream)
-    _ops._bump()
-    return out
+    return _ops.ops.rotation_matrix2d(center, angle, scale)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def get_rotation_matrix2d(center: torch.Tensor, angle: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """(B,2,3) rotation by ``angle`` degrees (counter-clockwise on screen) and per-axis ``scale``
     about ``center`` (x, y): T(c) @ R @ S @ T(-c)."""
@@ -117,17 +109,10 @@ class _FusedPerspective(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, points_src, points_dst):
-        from ... import _lib, _ops
-        from .._prelude import FUSED_VARIANT
+        from ... import _ops
 
-        ps, pd = points_src.contiguous(), points_dst.contiguous()
-        out = torch.empty((ps.shape[0], 3, 3), device=ps.device, dtype=ps.dtype)
-        with torch.cuda.device(ps.device):
-            _lib.call("kb200_perspective_from_points", ps.data_ptr(), pd.data_ptr(), out.data_ptr(), ps.shape[0],
-                      0 if ps.dtype == torch.float32 else 1, FUSED_VARIANT, torch.cuda.current_stream(ps.device).cuda_stream)
-        _ops._bump()
-        ctx.save_for_backward(ps, pd)
-        return out
+        ctx.save_for_backward(points_src, points_dst)
+        return _ops.ops.perspective_from_points(points_src, points_dst)
 
     @staticmethod
     def backward(ctx, gh):
@@ -140,7 +125,6 @@ class _FusedPerspective(torch.autograd.Function):
         return tuple(grads.pop(0) if need else None for need in ctx.needs_input_grad)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def get_perspective_transform(points_src: torch.Tensor, points_dst: torch.Tensor) -> torch.Tensor:
     """(B,3,3) homography taking the four ``points_src`` (B,4,2; x,y) onto ``points_dst``, scaled so
     that H[2,2] = 1: H = Q(dst) @ Q(src)^-1 with Q the unit-square-to-quad map (imgwarp.py:444-527).
@@ -157,5 +141,11 @@ def get_perspective_transform(points_src: torch.Tensor, points_dst: torch.Tensor
     fused_ok = (points_src.is_cuda and points_dst.is_cuda and points_src.dtype in (torch.float32, torch.float64)
                 and points_src.shape[0] >= FUSED_MIN_BATCH and os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") != "1")
     if fused_ok:
-        return _FusedPerspective.apply(points_src, points_dst)
+        needs_grad = torch.is_grad_enabled() and (points_src.requires_grad or points_dst.requires_grad)
+        if not needs_grad:
+            from ... import _ops
+
+            return _ops.ops.perspective_from_points(points_src, points_dst)
+        if not torch.compiler.is_compiling():  # the backward re-differentiates the torch op sequence: eager only
+            return _FusedPerspective.apply(points_src, points_dst)
     return _perspective_torch(points_src, points_dst)

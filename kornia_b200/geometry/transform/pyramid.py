@@ -51,7 +51,6 @@ def _fused_request(input: torch.Tensor, border_type: str, align_corners: bool, f
     return _binomial5x5().to(device=input.device, dtype=input.dtype), code
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def pyrdown(input: torch.Tensor, border_type: str = "reflect", align_corners: bool = False, factor: float = 2.0) -> torch.Tensor:
     """Blur with the 5x5 binomial kernel, then resample bilinearly onto (int(H / factor), int(W // factor))."""
     check_shape(input, ["B", "C", "H", "W"])
@@ -67,7 +66,6 @@ def pyrdown(input: torch.Tensor, border_type: str = "reflect", align_corners: bo
     return F.interpolate(blurred, size=size, mode="bilinear", align_corners=align_corners)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def pyrup(input: torch.Tensor, border_type: str = "reflect", align_corners: bool = False) -> torch.Tensor:
     """Resample bilinearly onto (2H, 2W), then blur with the 5x5 binomial kernel."""
     check_shape(input, ["B", "C", "H", "W"])

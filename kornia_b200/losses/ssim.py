@@ -9,7 +9,6 @@ from .. import metrics
 __all__ = ["ssim_loss", "SSIMLoss"]
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA ops
 def ssim_loss(img1: torch.Tensor, img2: torch.Tensor, window_size: int, max_val: float = 1.0, eps: float = 1e-12,
               reduction: str = "mean", padding: str = "same") -> torch.Tensor:
     """Structural dissimilarity ``clamp((1 - ssim) / 2, 0, 1)``, reduced by 'mean' | 'sum' | 'none'."""

@@ -33,7 +33,6 @@ def _composed(img1, img2, kernel, C1: float, C2: float, eps: float, crop):
     return num / (den + eps)
 
 
-@torch.compiler.disable  # opaque to torch.compile: a clean graph break around the CUDA op
 def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int, max_val: float = 1.0, eps: float = 1e-12,
          padding: str = "same") -> torch.Tensor:
     """Structural-similarity index map (B,C,H,W) of two image batches: Gaussian window of
@@ -59,21 +58,17 @@ def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int, max_val: floa
         m = _compute_padding([kernel.shape[-1], kernel.shape[-1]])
         crop = (-m[2], -m[3], -m[0], -m[1])
 
-    _ops._require_cuda(img1, "img1")
-    _ops._require_cuda(img2, "img2")
+    if not torch.compiler.is_compiling():
+        _ops._require_cuda(img1, "img1")
+        _ops._require_cuda(img2, "img2")
     B, C, H, W = img1.shape
     K = kernel.shape[-1]
     needs_grad = torch.is_grad_enabled() and (img1.requires_grad or img2.requires_grad)
     fused = (img1.dtype == torch.float32 and img2.dtype == torch.float32 and not needs_grad and K % 2 == 1 and 3 <= K <= 11
              and K // 2 < min(H, W) and img1.numel() > 0)
     if fused:
-        a, b = img1.contiguous(), img2.contiguous()
-        out = torch.empty_like(a)
         try:
-            with torch.cuda.device(a.device), _ops._Timed("ssim_forward", a):
-                _lib.call("kb200_ssim_forward", a.data_ptr(), b.data_ptr(), kernel.contiguous().data_ptr(), out.data_ptr(), B * C, H, W, K,
-                          float(C1), float(C2), float(eps), _lib.F32, _ops._stream(a))
-            _ops._bump()
+            out = _ops.ops.ssim_fwd(img1, img2, kernel, float(C1), float(C2), float(eps))
             return out if crop is None else torch.nn.functional.pad(out, crop)
         except _lib.Unsupported:
             pass

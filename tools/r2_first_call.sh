@@ -16,7 +16,7 @@ export PYTHONUNBUFFERED=1
 step() { echo "=== $1" | tee -a "$OUT/steps.log"; }
 
 step "1 gpu tests of the default build"
-timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider > "$OUT/pytest_gpu.log" 2>&1; echo "rc=$?" >> "$OUT/pytest_gpu.log"
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > "$OUT/pytest_gpu.log" 2>&1; echo "rc=$?" >> "$OUT/pytest_gpu.log"
 tail -3 "$OUT/pytest_gpu.log" | tee -a "$OUT/steps.log"
 
 step "2 bench lines (headline, blur, fwd+bwd) and the CPU arm"
@@ -56,6 +56,6 @@ KB200_BWD_V2=1 timeout 400 python bench.py --workload warp_bwd --no-cpu-baseline
 timeout 400 python bench.py --workload ingest --no-cpu-baseline > "$OUT/bench_ingest.json" 2> "$OUT/bench_ingest.err"; echo "ingest rc=$?" | tee -a "$OUT/steps.log"
 
 step "8 compute-sanitizer memcheck: default kernels + ingest warps, then the same workload through the opt-in kernels"
-timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py > "$OUT/memcheck_default.txt" 2>&1; tail -3 "$OUT/memcheck_default.txt" | tee -a "$OUT/steps.log"
-KB200_OPTIN=all timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py > "$OUT/memcheck_optin.txt" 2>&1; tail -3 "$OUT/memcheck_optin.txt" | tee -a "$OUT/steps.log"
+timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py > "$OUT/memcheck_default.txt" 2>&1; tail -3 "$OUT/memcheck_default.txt" | tee -a "$OUT/steps.log"
+KB200_OPTIN=all timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py > "$OUT/memcheck_optin.txt" 2>&1; tail -3 "$OUT/memcheck_optin.txt" | tee -a "$OUT/steps.log"
 ls -la "$OUT" | tee -a "$OUT/steps.log"
