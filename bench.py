@@ -197,68 +197,36 @@ def run_reference(args) -> None:
 
 # ------------------------------------------------------------------------------------------ ours
 def host_ring_samples(B: int, chunk: int, available_bytes=None, local_ranks=None) -> int:
-    """How many samples of the batch each rank keeps in pinned host memory (source and destination each): all B when
-    a third of this rank's share of the available host memory holds both buffers, else the largest whole number of
-    chunks that does (at least one)."""
-    if available_bytes is None:
-        try:
-            import psutil
+    """How many samples of the batch each rank keeps in pinned host memory (source and destination each); the arithmetic
+    lives in the library (kornia_b200/streaming.py:host_ring_samples)."""
+    from kornia_b200.streaming import host_ring_samples as ring
 
-            available_bytes = psutil.virtual_memory().available
-        except Exception:
-            return B
-    if local_ranks is None:
-        local_ranks = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
-    per_sample = 2 * C_IMG * H_IMG * W_IMG * 4
-    fit = int(available_bytes / max(local_ranks, 1) / 3) // per_sample
-    if fit >= B:
-        return B
-    return max(chunk, fit // chunk * chunk) if B > chunk else B
+    return ring(B, chunk, 2 * C_IMG * H_IMG * W_IMG * 4, available_bytes, local_ranks)
 
 
 def e2e_run(K, M_dev, B, steps, warmup, chunk, dev):
-    """Host-buffer throughput: pinned src -> device -> warp -> pinned dst, chunked over 3 streams."""
+    """Host-buffer throughput through the library's own host pipeline (kornia_b200.streaming.warp_perspective_host: pinned
+    src -> device -> warp -> pinned dst, chunked over 3 streams, the process bound to the GPU's NUMA node)."""
+    from kornia_b200 import streaming
+
     n_el = B * C_IMG * H_IMG * W_IMG
+    numa = streaming.bind_to_device_numa_node(dev.index)  # before the pinned allocations: their pages follow the policy
     # Host side of the step: the whole batch in pinned memory (2 x 6.37 GB per rank at B=256).  When the box cannot
     # spare that for every local rank (8 ranks would lock 102 GB), the batch is streamed through a shorter pinned ring
     # of whole chunks instead: the bytes crossing PCIe per step are the same, the note says which form ran.
     HB = host_ring_samples(B, chunk)
     try:
-        src_h = torch.empty((HB, C_IMG, H_IMG, W_IMG), dtype=torch.float32, pin_memory=True)
-        dst_h = torch.empty((HB, C_IMG, H_IMG, W_IMG), dtype=torch.float32, pin_memory=True)
+        src_h = streaming.pinned_empty((HB, C_IMG, H_IMG, W_IMG), torch.float32, dev.index)
+        dst_h = streaming.pinned_empty((HB, C_IMG, H_IMG, W_IMG), torch.float32, dev.index)
     except RuntimeError as e:  # not enough lockable host memory
         return None, f"pinned allocation failed: {e}"
-    # cheap deterministic fill (content does not affect timing)
+    # cheap deterministic fill (content does not affect timing); touching every page also places it
     src_h.view(-1)[: 1 << 20].uniform_()
     src_h.view(-1)[1 << 20:] = 0.5
-    s_in, s_k, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    nbuf = 3
-    d_in = [torch.empty((chunk, C_IMG, H_IMG, W_IMG), device=dev) for _ in range(nbuf)]
-    d_out = [None] * nbuf
-    ev_in = [torch.cuda.Event() for _ in range(nbuf)]
-    ev_k = [torch.cuda.Event() for _ in range(nbuf)]
-    ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+    dst_h.zero_()
 
     def one_step():
-        for i, b0 in enumerate(range(0, B, chunk)):
-            j = i % nbuf
-            n = min(chunk, B - b0)
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(ev_k[j])  # the kernel that last read this input buffer is done
-                h0 = b0 % HB  # == b0 when the whole batch is pinned (HB is a multiple of chunk)
-                d_in[j][:n].copy_(src_h[h0:h0 + n], non_blocking=True)
-                ev_in[j].record(s_in)
-            with torch.cuda.stream(s_k):
-                s_k.wait_event(ev_in[j])
-                s_k.wait_event(ev_out[j])  # previous result in this slot has left the device
-                d_out[j] = K.warp_perspective(d_in[j][:n], M_dev[b0:b0 + n], (H_IMG, W_IMG))
-                ev_k[j].record(s_k)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_k[j])
-                dst_h[h0:h0 + n].copy_(d_out[j], non_blocking=True)
-                ev_out[j].record(s_out)
-        for s in (s_in, s_k, s_out):
-            torch.cuda.current_stream(dev).wait_stream(s)
+        streaming.warp_perspective_host(src_h, M_dev, (H_IMG, W_IMG), out=dst_h, device=dev, chunk=chunk, logical_batch=B, synchronize=False)
 
     for _ in range(warmup):
         one_step()
@@ -273,7 +241,8 @@ def e2e_run(K, M_dev, B, steps, warmup, chunk, dev):
     ms = t0.elapsed_time(t1) / steps
     del src_h, dst_h
     host = "whole batch pinned" if HB == B else f"pinned ring of {HB} samples reused {B / HB:.1f}x per step (host memory per local rank)"
-    return ms, f"pinned host buffers ({host}), chunk={chunk} samples, 3 streams (H2D / kernel / D2H), {n_el * 4} B each way per step"
+    return ms, (f"kornia_b200.streaming.warp_perspective_host: pinned host buffers ({host}), chunk={chunk} samples, 3 streams (H2D / kernel / D2H), "
+                f"{n_el * 4} B each way per step; NUMA binding {numa}")
 
 
 def max_over_ranks_or_none(dist, ms, note, device):
