@@ -63,10 +63,14 @@ def perspective_from_quads(src_q: torch.Tensor, dst_q: torch.Tensor) -> torch.Te
     return torch.cat([hvec, torch.ones(B, 1, dtype=torch.float64)], 1).view(B, 3, 3).float()
 
 
-def make_homographies(B: int, seed: int) -> torch.Tensor:
+def make_homographies_hw(B: int, seed: int, Hh: int, Ww: int) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
-    quad = torch.tensor([[0.0, 0.0], [W_IMG - 1.0, 0.0], [W_IMG - 1.0, H_IMG - 1.0], [0.0, H_IMG - 1.0]]).expand(B, 4, 2)
+    quad = torch.tensor([[0.0, 0.0], [Ww - 1.0, 0.0], [Ww - 1.0, Hh - 1.0], [0.0, Hh - 1.0]]).expand(B, 4, 2)
     return perspective_from_quads(quad, quad + 8.0 * torch.randn(B, 4, 2, generator=g))
+
+
+def make_homographies(B: int, seed: int) -> torch.Tensor:
+    return make_homographies_hw(B, seed, H_IMG, W_IMG)
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -193,6 +197,144 @@ def run_reference(args) -> None:
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ side legs (untimed context)
+def bandlimited(shape, dev, seed: int) -> torch.Tensor:
+    """SURVEY 8d band-limited set: per (b,c) a sum of 6 sinusoids of <= 8 cycles per image with random phases, scaled to [0,1]."""
+    B, C, Hh, Ww = shape
+    g = torch.Generator().manual_seed(seed)
+    fx = torch.randint(0, 9, (B, C, 6, 1, 1), generator=g).float().to(dev)
+    fy = torch.randint(0, 9, (B, C, 6, 1, 1), generator=g).float().to(dev)
+    ph = (torch.rand(B, C, 6, 1, 1, generator=g) * 2 * math.pi).to(dev)
+    ys = torch.linspace(0, 1, Hh, device=dev).view(1, 1, 1, Hh, 1)
+    xs = torch.linspace(0, 1, Ww, device=dev).view(1, 1, 1, 1, Ww)
+    img = torch.sin(2 * math.pi * (fx * xs + fy * ys) + ph).sum(2)
+    lo, hi = img.amin((2, 3), keepdim=True), img.amax((2, 3), keepdim=True)
+    return (img - lo) / (hi - lo).clamp_min(1e-6)
+
+
+def _rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def parity_table(K, dev) -> dict:
+    """SURVEY 8d "parity reported alongside": rel-L2 of (ours vs the reference composition in fp32 on the SAME device, cuDNN
+    off), (ours vs the fp64 composition) and (fp32 composition vs fp64) for out, d/dsrc, d/dM, on white-noise and band-limited
+    images at native resolution (forward 1080p, gradients at the cfg4 720p shape; two samples each, the bench homographies).
+    The composition is oracle/kornia_restated.py (the ATen calls the reference issues): checker only, nothing here is timed."""
+    from oracle import kornia_restated as R
+
+    table = {"tolerance": 1e-4, "ref": "oracle/kornia_restated.py on cuda, cudnn disabled", "sets": {}}
+    with torch.backends.cudnn.flags(enabled=False):
+        for name in ("white", "bandlimited"):
+            rows = {}
+            # forward, 1080p
+            shape = (2, C_IMG, H_IMG, W_IMG)
+            src = torch.rand(shape, device=dev) if name == "white" else bandlimited(shape, dev, 11)
+            M = make_homographies(2, 77).to(dev)
+            with torch.no_grad():
+                ours = K.warp_perspective(src, M, (H_IMG, W_IMG))
+                r32 = R.warp_perspective(src, M, (H_IMG, W_IMG))
+                r64 = R.warp_perspective(src.double(), M.double(), (H_IMG, W_IMG))
+            rows["out_1080p"] = {"ours_vs_ref32": _rel(ours, r32), "ours_vs_fp64": _rel(ours, r64), "ref32_vs_fp64": _rel(r32, r64),
+                                 "max_abs_ours_vs_ref32": float((ours - r32).abs().max())}
+            del ours, r32, r64, src
+            # gradients, 720p (cfg4): mean squared error against a band-limited target (smooth set), fixed random cotangent (white)
+            Hh, Ww = 720, 1280
+            shape = (2, C_IMG, Hh, Ww)
+            src = torch.rand(shape, device=dev) if name == "white" else bandlimited(shape, dev, 12)
+            g = torch.Generator().manual_seed(7)
+            quad = torch.tensor([[0.0, 0.0], [Ww - 1.0, 0.0], [Ww - 1.0, Hh - 1.0], [0.0, Hh - 1.0]]).expand(2, 4, 2)
+            M = perspective_from_quads(quad, quad + 8.0 * torch.randn(2, 4, 2, generator=g)).to(dev)
+            target = bandlimited(shape, dev, 13)
+            cot = torch.randn(shape, device=dev)
+
+            def grads(impl, dt):
+                s = src.to(dt).detach().requires_grad_(True)
+                m = M.to(dt).detach().requires_grad_(True)
+                out = impl.warp_perspective(s, m, (Hh, Ww))
+                if name == "white":
+                    out.backward(cot.to(dt))
+                else:
+                    ((out - target.to(dt)) ** 2).mean().backward()
+                return out.detach(), s.grad, m.grad
+
+            o, r32, r64 = grads(K, torch.float32), grads(R, torch.float32), grads(R, torch.float64)
+            for key, i in (("out_720p", 0), ("dsrc_720p", 1), ("dM_720p", 2)):
+                rows[key] = {"ours_vs_ref32": _rel(o[i], r32[i]), "ours_vs_fp64": _rel(o[i], r64[i]), "ref32_vs_fp64": _rel(r32[i], r64[i])}
+            table["sets"][name] = rows
+            del o, r32, r64, src, target, cot
+    torch.cuda.empty_cache()
+    return table
+
+
+def _time_gpu(fn, dev, warmup: int = 2, iters: int = 5) -> float:
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(iters):
+        fn()
+    t1.record()
+    torch.cuda.synchronize(dev)
+    return t0.elapsed_time(t1) / iters
+
+
+def torch_gpu_legs(workload: str, dev, sample_b: int = 32, with_compile: bool = True) -> dict:
+    """The reference's own torch composition ON THIS GPU ("the real bar to beat"): oracle/kornia_restated.py in
+    eager mode and under torch.compile, on a bounded sample of the workload (per-pixel metric; the composition's temporaries
+    -- a (B,h,w,2) grid plus ~15 elementwise intermediates -- are why the sample is smaller than the batch).  Reported context,
+    never part of value / e2e."""
+    from oracle import kornia_restated as R
+
+    out = {}
+    torch.manual_seed(5)
+    if workload == "warp":
+        x = torch.rand(sample_b, C_IMG, H_IMG, W_IMG, device=dev)
+        M = make_homographies(sample_b, 5).to(dev)
+        fn, pix = (lambda f: (lambda: f(x, M, (H_IMG, W_IMG)))), sample_b * H_IMG * W_IMG
+        target = R.warp_perspective
+    elif workload == "blur":
+        x = torch.rand(sample_b, C_IMG, H_IMG, W_IMG, device=dev)
+        fn, pix = (lambda f: (lambda: f(x, (11, 11), (2.0, 2.0), "reflect", True))), sample_b * H_IMG * W_IMG
+        target = R.gaussian_blur2d
+    elif workload == "warp_bwd":
+        Hh, Ww = 720, 1280
+        x = torch.rand(sample_b, C_IMG, Hh, Ww, device=dev)
+        M = make_homographies_hw(sample_b, 5, Hh, Ww).to(dev)
+        cot = torch.rand(sample_b, C_IMG, Hh, Ww, device=dev) - 0.5
+
+        def fn(f):
+            def step():
+                s, m = x.detach().requires_grad_(True), M.detach().requires_grad_(True)
+                return torch.autograd.grad(f(s, m, (Hh, Ww)), [s, m], grad_outputs=cot)
+            return step
+
+        pix, target = sample_b * Hh * Ww, R.warp_perspective
+    else:
+        return out
+    sample = f"B={sample_b} of the workload, CUDA events, 2 warm-ups + 5 iterations"
+    try:
+        ms = _time_gpu(fn(target), dev)
+        out["torch_eager_gpu"] = {"value": pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms": ms, "sample": sample, "what": "oracle/kornia_restated.py (the reference's ATen call sequence) in torch eager on this GPU"}
+    except Exception as e:  # out of memory on a busy box, ...
+        out["torch_eager_gpu"] = {"value": None, "error": f"{type(e).__name__}: {str(e)[:160]}"}
+    if with_compile:
+        try:
+            torch._dynamo.reset()
+            compiled = torch.compile(target)
+            t_c0 = time.perf_counter()
+            ms = _time_gpu(fn(compiled), dev)
+            out["torch_compile_gpu"] = {"value": pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms": ms, "sample": sample,
+                                        "what": "torch.compile (inductor) of the same composition", "compile_and_measure_s": time.perf_counter() - t_c0}
+        except Exception as e:  # inductor toolchain missing / failing on the box
+            out["torch_compile_gpu"] = {"value": None, "error": f"{type(e).__name__}: {str(e)[:160]}"}
+    del x
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------ ours
@@ -347,6 +489,12 @@ def run_ours(args) -> None:
                "sample": f"3 steps of B=32x3x1080x1920 ({ms:.0f} ms each) with torch CPU ops, {cores} of {os.cpu_count()} threads "
                          "(best of a calibration): oracle/kornia_restated.py"}
 
+    side = {}
+    if world == 1 and not args.no_side_legs:
+        del src
+        torch.cuda.empty_cache()
+        side["parity"] = parity_table(K, dev)
+        side["same_gpu_reference"] = torch_gpu_legs("warp", dev, with_compile=not args.no_compile_leg)
     bytes_step = B * C_IMG * H_IMG * W_IMG * 4
     line = {
         "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -367,6 +515,7 @@ def run_ours(args) -> None:
         "clocks": clk.summary(),
         "checksum": checksum,
     }
+    line.update(side)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -445,11 +594,173 @@ def run_extra(args) -> None:
                          "kernel_ms": k_ms, "achieved": (bytes_per_pix * pix / (k_ms * 1e-3) / 1e9) if k_ms else None,
                          "frac": (bytes_per_pix * pix / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None},
             "gpu_launches": launches, "clocks": clk.summary()}
+    if not args.no_side_legs and args.workload in ("blur", "warp_bwd"):
+        line["same_gpu_reference"] = torch_gpu_legs(args.workload, dev, sample_b=32 if args.workload == "blur" else 16, with_compile=not args.no_compile_leg)
+        if args.workload == "warp_bwd":
+            line["parity"] = parity_table(K, dev)
     if args.workload == "warp_bwd":  # the timed kernel is the backward alone: 36 B/pixel (read gout + src, write gsrc)
         line["roofline"].update({"kernel": "warp_backward (+ d/dM reduction)", "kernel_bytes_per_pixel": 36.0,
                                  "achieved": (36.0 * pix / (k_ms * 1e-3) / 1e9) if k_ms else None,
                                  "frac": (36.0 * pix / (k_ms * 1e-3) / 1e9 / peak) if k_ms else None})
     print(json.dumps(line), flush=True)
+
+
+def run_small(args) -> None:
+    """The only operating point the reference PUBLISHES (benchmarks/README.md:154-157; benchmarks/geometry/flagship.py): 256x256,
+    batch 32, fp32, throughput in images/s of back-to-back calls -- host launch cost included, the reference's own method
+    (torch.utils.benchmark blocked_autorange: wall clock over many calls with one sync at the end).  Published on an RTX PRO 6000
+    Blackwell: warp_perspective 96 022 eager / 232 170 compiled, warp_affine 120 089 / 217 083, rotate 58 357 / 159 196
+    (torchvision 298 016), get_perspective_transform 78 071 / 431 034 solves/s.  One JSON line; `vs_published` = ours / published."""
+    import kornia_b200 as K
+    from kornia_b200 import _lib, _ops
+    from oracle import kornia_restated as R
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    _lib.load()
+    b, h, w = 32, 256, 256
+    torch.manual_seed(0)
+    x = torch.rand(b, 3, h, w, device=dev)
+    angle = torch.full((b,), 30.0, device=dev)
+    center = torch.tensor([[w / 2, h / 2]], device=dev).expand(b, 2).contiguous()
+    scale = torch.ones(b, 2, device=dev)
+    quad = torch.tensor([[[0.0, 0.0], [w - 1.0, 0.0], [w - 1.0, h - 1.0], [0.0, h - 1.0]]]).expand(b, 4, 2).contiguous()
+    dst = (quad + 8.0 * torch.randn(b, 4, 2, generator=torch.Generator().manual_seed(0))).to(dev)
+    quad = quad.to(dev)
+    m_aff = K.geometry.transform.get_rotation_matrix2d(center, angle, scale)
+    h_mat = K.geometry.transform.get_perspective_transform(quad, dst)
+    published = {"warp_perspective": (96022, 232170), "warp_affine": (120089, 217083), "rotate": (58357, 159196), "get_perspective_transform": (78071, 431034)}
+
+    def cases(impl):
+        return {"warp_perspective": lambda: impl.warp_perspective(x, h_mat, (h, w)),
+                "warp_affine": lambda: impl.warp_affine(x, m_aff, (h, w)),
+                "rotate": (lambda: impl.geometry.transform.rotate(x, angle)) if impl is K else (lambda: impl.rotate(x, angle)),
+                "get_perspective_transform": (lambda: impl.geometry.transform.get_perspective_transform(quad, dst)) if impl is K else (lambda: impl.get_perspective_transform(quad, dst))}
+
+    def throughput(fn, seconds=1.0):
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize(dev)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            for _ in range(100):
+                fn()
+            n += 100
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            if dt >= seconds:
+                return b * n / dt, dt / n * 1e6
+
+    rows = {}
+    with torch.no_grad():
+        launches0 = _ops.launch_count
+        for name, fn in cases(K).items():
+            ips, us = throughput(fn)
+            rows[name] = {"ours_img_s": ips, "ours_us_per_call": us, "published_eager": published[name][0], "published_compiled": published[name][1],
+                          "vs_published_eager": ips / published[name][0], "vs_published_compiled": ips / published[name][1]}
+        launches = _ops.launch_count - launches0
+        if not args.no_side_legs:
+            for name, fn in cases(R).items():  # the reference composition in torch eager on THIS GPU
+                ips, us = throughput(fn, 0.5)
+                rows[name].update({"torch_eager_here_img_s": ips, "vs_torch_eager_here": rows[name]["ours_img_s"] / ips})
+    head = rows["warp_perspective"]
+    line = {"metric": "img/s warp_perspective 32x3x256x256 fwd bilinear fp32 (back-to-back calls, wall clock, host cost included)", "value": head["ours_img_s"],
+            "unit": "img/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": head["vs_published_compiled"],
+            "config": {"workload": "benchmarks/geometry/flagship.py operating point: batch 32, 256x256, fp32; rotate 30 deg about the centre, corner quad jittered by 8*randn px",
+                       "baseline": "benchmarks/README.md:154-157, RTX PRO 6000 Blackwell, kornia + torch.compile (other hardware: published context, not a same-box comparison)",
+                       "timing": ">= 1 s of back-to-back calls per op, one synchronize per 100 calls, wall clock"},
+            "ops": rows, "gpu_launches": launches}
+    print(json.dumps(line), flush=True)
+
+
+def run_scatter_gather(args) -> None:
+    """cfg5 as BASELINE.json words it ("batch-sharded ... via NCCL"), the secondary numbers of SURVEY 8d: the batch starts and ends
+    on rank 0.  (1) kornia_b200.sharding.sharded_apply: ONE NCCL scatter of the inputs, the warp on every rank, ONE NCCL gather of
+    the outputs -- timed with CUDA events on every rank, max over ranks, reported with the NVLink GB/s the two collectives
+    achieve; (2) strong scaling: the same global batch with shards already resident (what (1) costs without its collectives)."""
+    import torch.distributed as dist
+
+    import kornia_b200 as K
+    from kornia_b200 import _lib
+    from kornia_b200.sharding import shard_range, sharded_apply
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.load()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29512", rank=0, world_size=1)
+    Bg = args.global_batch or 64 * world  # rank 0 holds the whole input and output: 2 x 24.9 MB per sample
+    torch.manual_seed(1000)
+    src = torch.rand(Bg, C_IMG, H_IMG, W_IMG, device=dev) if rank == 0 else None
+    M = make_homographies(Bg, 1000).to(dev)
+    dsize = (H_IMG, W_IMG)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    def max_ms(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        barrier()
+        return max_ms(t0.elapsed_time(t1) / steps)
+
+    steps, warmup = max(2, min(args.steps, 5)), max(2, min(args.warmup, 3))
+
+    def sg_step():
+        return sharded_apply(lambda s, m: K.warp_perspective(s, m, dsize), (src, M if rank == 0 else None), batch=Bg,
+                             shapes=[(C_IMG, H_IMG, W_IMG), (3, 3)], dtypes=[torch.float32, torch.float32], device=dev, root=0)
+
+    out = sg_step()
+    checksum = float(out[0, :, ::97, ::89].sum()) if rank == 0 else 0.0
+    del out
+    sg_ms = timed(sg_step, steps, warmup)
+    # strong scaling: same global batch, shard already resident on its rank (generated from the same seed, then sliced)
+    a, b = shard_range(Bg, world, rank)
+    if rank == 0:
+        shard = src[a:b].clone()
+        del src
+    else:
+        shard = torch.rand(b - a, C_IMG, H_IMG, W_IMG, device=dev)
+    src = None
+    Ms = M[a:b].contiguous()
+    res_ms = timed(lambda: K.warp_perspective(shard, Ms, dsize), max(args.steps, 5), max(args.warmup, 3))
+    if rank == 0:
+        pix = Bg * H_IMG * W_IMG
+        moved = (Bg - (b - a)) * C_IMG * H_IMG * W_IMG * 4  # bytes leaving rank 0 in the scatter (= bytes arriving in the gather)
+        coll_ms = max(sg_ms - res_ms, 1e-6)
+        line = {"metric": "Mpix/s warp_perspective global batch on rank 0: NCCL scatter -> warp on every rank -> NCCL gather", "value": pix / (sg_ms * 1e-3) / 1e6,
+                "unit": "Mpix/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": sg_ms, "higher_is_better": True, "scaling": "strong",
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"warp_perspective fwd global B={Bg}x3x1080x1920 held by rank 0 (BASELINE.json configs[4] 'via NCCL', secondary number of SURVEY 8d)",
+                           "global_batch": Bg, "parallelism": f"kornia_b200.sharding.sharded_apply over {world} ranks: 1 scatter + 1 gather, no other collective"},
+                "collectives": {"bytes_out_of_rank0_per_direction": moved, "ms_scatter_plus_gather": coll_ms,
+                                "nvlink_GBps_per_direction_rank0": moved / (coll_ms / 2 * 1e-3) / 1e9,
+                                "note": "rank 0's NVLink ports serialise the scatter and the gather: 2 x bytes over its 900 GB/s per direction"},
+                "strong_scaling_resident": {"value": pix / (res_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": res_ms,
+                                            "note": f"same global batch, shards of {b - a} samples already on their ranks, max over ranks"},
+                "checksum": checksum}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
 
 
 def main() -> None:
@@ -460,13 +771,21 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU")
     ap.add_argument("--e2e-chunk", type=int, default=16)
+    ap.add_argument("--global-batch", type=int, default=0, help="scatter_gather workload: samples held by rank 0 (default 64 per rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["warp", "blur", "warp_bwd", "ingest"], default="warp",
+    ap.add_argument("--no-side-legs", action="store_true", help="skip the untimed context legs (parity table, torch eager / torch.compile of the "
+                    "reference composition on the same GPU)")
+    ap.add_argument("--no-compile-leg", action="store_true", help="skip only the torch.compile leg (inductor needs a host compiler and ~1 min)")
+    ap.add_argument("--workload", choices=["warp", "blur", "warp_bwd", "ingest", "small", "scatter_gather"], default="warp",
                     help="warp = the headline (BASELINE.json configs[1]); blur / warp_bwd = configs[2] / configs[3]; ingest = the uint8 wire-format warp "
                          "(SURVEY 8f row 4, not a BASELINE config); single GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "small":
+        run_small(args)
+    elif args.workload == "scatter_gather":
+        run_scatter_gather(args)
     elif args.workload != "warp":
         run_extra(args)
     else:

@@ -9,26 +9,11 @@ no CPU path and no fallback -- a missing library or a CPU tensor raises.
 """
 from __future__ import annotations
 
-from . import core, filters, geometry, losses, metrics
+from . import config, core, filters, geometry, losses, metrics, streaming
 from .filters import filter2d, filter2d_separable, gaussian_blur2d
 from .geometry.transform import remap, warp_affine, warp_perspective
 
 __version__ = "0.1.0"
-
-# Kernels written after the round-1 GPU budget was spent are opt-in, one switch each.
-# KB200_OPTIN=all turns every one of them on for this process, so that the WHOLE GPU test suite can be run through them
-# (`KB200_OPTIN=all python -m pytest tests -m gpu`): the C library reads the switches with getenv at call time.
-OPTIN_SWITCHES = ("KB200_SEP_VWALK", "KB200_SSIM_VWALK", "KB200_TILED_GRADIENT", "KB200_BWD_V2", "KB200_REMAP_V2", "KB200_FUSED_UNDISTORT",
-                  "KB200_FUSED_PYRDOWN", "KB200_FAST_FILTER_BWD")
-# Switches promoted to defaults: a kernel that has passed its bit-identity tests on hardware and measured faster is turned on
-# by adding its switch here (one line, no C change: every switch is read with getenv at call time); NAME=0 in the environment
-# still selects the kernel it replaced.  Empty until the first GPU call of round 2 (tools/r2_first_call.sh) has reported.
-DEFAULT_ON: tuple = ()
-for _name in DEFAULT_ON:
-    __import__("os").environ.setdefault(_name, "1")
-if __import__("os").environ.get("KB200_OPTIN") == "all":
-    for _name in OPTIN_SWITCHES:
-        __import__("os").environ.setdefault(_name, "1")
 
 _PATCHED = {}
 
@@ -82,4 +67,4 @@ def uninstall() -> None:
 
 
 __all__ = ["warp_perspective", "warp_affine", "remap", "filter2d", "filter2d_separable", "gaussian_blur2d", "install",
-           "uninstall", "core", "filters", "geometry", "losses", "metrics"]
+           "uninstall", "config", "core", "filters", "geometry", "losses", "metrics", "streaming"]

@@ -31,6 +31,8 @@ SIGNATURES = {
     "kb200_last_error": (ctypes.c_char_p, []),
     "kb200_last_warp_variant": (ctypes.c_char_p, []),
     "kb200_last_warp_launches": (_i, []),
+    "kb200_set_option": (_i, [ctypes.c_char_p, _i]),
+    "kb200_get_option": (_i, [ctypes.c_char_p]),
     "kb200_warp_forward": (_i, [_vp] * 6 + [_i] * 12 + [_vp]),
     "kb200_warp_prelude": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),
     "kb200_warp_prelude_backward": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
@@ -85,23 +87,11 @@ def load() -> ctypes.CDLL:
     return _lib
 
 
-def _opaque(fn):
-    """Keep torch.compile / dynamo out of the ctypes layer: the ops become opaque graph breaks (the
-    reference's tracing branches are out of scope; north_star: no multi-backend dispatch)."""
-    try:
-        import torch
-
-        return torch.compiler.disable(fn)
-    except Exception:  # very old torch
-        return fn
-
-
 class Unsupported(RuntimeError):
     """The C entry point declined a valid request (status KB200_EUNSUPPORTED): the caller may route it
     through other entry points of the library."""
 
 
-@_opaque
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and turn a non-zero status into ``RuntimeError``."""
     lib = load()

@@ -115,7 +115,7 @@ def _autograd(name: str, backward, setup_context) -> None:
 def _once_differentiable(name: str) -> None:
     """Backward operators are first-order only: differentiating THROUGH one (create_graph=True: gradient penalties,
     Hessian-vector products) raises instead of silently dropping the second-order terms.  The reference supports double
-    backward through its torch-op composition; set KORNIA_B200_TORCH_PRELUDE=1 for the matrix chain, there is no such
+    backward through its torch-op composition; ``config.set("torch_prelude", 1)`` gives the matrix chain as torch ops, there is no such
     switch for the image kernels."""
 
     def backward(ctx, *grads):
@@ -545,7 +545,9 @@ def sepfilter(x, kx, ky, border, same):
 
 
 def fast_filter_bwd_enabled() -> bool:
-    return os.environ.get("KB200_FAST_FILTER_BWD") == "1"
+    from . import config
+
+    return config.enabled("fast_filter_bwd")
 
 
 def _sep_input_gradient(gout: torch.Tensor, kx: torch.Tensor, ky: torch.Tensor, border: int) -> torch.Tensor:

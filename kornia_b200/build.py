@@ -93,7 +93,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for f in os.listdir(obj_dir):  # objects of sources that no longer exist must not be linked by a later glob or linger
         if f.endswith(".o") and f not in known:
             os.remove(os.path.join(obj_dir, f))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
+    cmd = [nvcc, "-shared", "-Xfatbin", "-compress-all", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)

@@ -12,7 +12,7 @@
 #include "filter2d_tiled.cuh"
 #include "remap_tiled.cuh"
 #include "gradient.cuh"
-#include "ssim_tiled.cuh"
+#include "ssim_vwalk.cuh"
 
 namespace kb200 {
 
@@ -25,6 +25,28 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---------------------------------------------------------------- kernel-selection switches (common.cuh: enum Option)
+static const char* const OPTION_NAMES[OPT_COUNT] = {"tma", "tiled_filter", "square_tiles", "sep_vwalk", "tiled_gradient", "u8_tiled", "bwd_v3"};
+static const int OPTION_DEFAULTS[OPT_COUNT] = {1, 1, 1, -1, 1, 1, 0};
+static int g_options[OPT_COUNT];
+static const bool g_options_ready = [] {  // once, when the library is loaded: KB200_<NAME>=<int> overrides the default
+  for (int i = 0; i < OPT_COUNT; ++i) {
+    char env[64] = "KB200_";
+    size_t n = strlen(env);
+    for (const char* c = OPTION_NAMES[i]; *c && n + 1 < sizeof(env); ++c) env[n++] = (char)((*c >= 'a' && *c <= 'z') ? *c - 32 : *c);
+    env[n] = 0;
+    const char* v = getenv(env);
+    g_options[i] = (v && v[0]) ? atoi(v) : OPTION_DEFAULTS[i];
+  }
+  return true;
+}();
+int option(Option o) { return __atomic_load_n(&g_options[o], __ATOMIC_RELAXED); }
+static int option_index(const char* name) {
+  for (int i = 0; name && i < OPT_COUNT; ++i)
+    if (strcmp(name, OPTION_NAMES[i]) == 0) return i;
+  return -1;
 }
 
 static int post_launch(const char* what) {
@@ -162,6 +184,17 @@ const char* kb200_last_error(void) { return g_err; }
 const char* kb200_last_warp_variant(void) { return g_variant; }
 int kb200_last_warp_launches(void) { return g_warp_launches; }
 
+int kb200_set_option(const char* name, int value) {
+  const int i = option_index(name);
+  KB_CHECK_ARG(i >= 0, "unknown option '%s'", name ? name : "(null)");
+  __atomic_store_n(&g_options[i], value, __ATOMIC_RELAXED);
+  return KB200_OK;
+}
+int kb200_get_option(const char* name) {
+  const int i = option_index(name);
+  return i < 0 ? (-2147483647 - 1) : option((Option)i);
+}
+
 int kb200_warp_forward(const void* src, const void* m, const void* bx, const void* by, const void* fill, void* out, int B,
                        int C, int H, int W, int h, int w, int Bm, int projective, int interp, int pad, int align_corners,
                        int dtype, void* stream) {
@@ -173,8 +206,7 @@ int kb200_warp_forward(const void* src, const void* m, const void* bx, const voi
   if (dtype == KB200_F32) {
     // fast path: TMA-staged source tiles (warp_tma.cuh); declines shapes / modes it does not cover.
     // KB200_DISABLE_TMA=1 forces the generic kernel (tests compare the two bit for bit).
-    const char* off = getenv("KB200_DISABLE_TMA");
-    rc = (off && off[0] == '1') ? KB200_EUNSUPPORTED : warp_tma_forward((const float*)src, (const float*)m, (const float*)bx, (const float*)by, (const float*)fill,
+    rc = !option(OPT_TMA) ? KB200_EUNSUPPORTED : warp_tma_forward((const float*)src, (const float*)m, (const float*)bx, (const float*)by, (const float*)fill,
                           (float*)out, B, C, H, W, h, w, Bm, projective, interp, pad, align_corners, st);
     if (rc != KB200_EUNSUPPORTED) {
       g_variant = "tma_tile";
@@ -250,9 +282,6 @@ int kb200_remap_forward(const void* src, const void* map_x, const void* map_y, v
   KB_CHECK_ARG(map_x && map_y && out, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == KB200_F32) {
-    rc = remap_warp_forward((const float*)src, (const float*)map_x, (const float*)map_y, nullptr, (float*)out, B, C, H, W, h, w, Bmap, normalized,
-                            interp, pad, align_corners, st);  // opt-in (KB200_REMAP_V2=1), declines otherwise
-    if (rc != KB200_EUNSUPPORTED) return rc;
     rc = remap_tiled_forward((const float*)src, (const float*)map_x, (const float*)map_y, (float*)out, B, C, H, W, h, w, Bmap, normalized,
                              interp, pad, align_corners, st);
     if (rc != KB200_EUNSUPPORTED) return rc;
@@ -267,9 +296,7 @@ int kb200_undistort_forward(const void* src, const void* lens, void* out, int B,
   KB_CHECK_ARG(dtype == KB200_F32 || dtype == KB200_F64, "bad dtype %d", dtype);
   int rc = KB200_EUNSUPPORTED;
   if (dtype == KB200_F32) {
-    rc = remap_warp_forward((const float*)src, nullptr, nullptr, (const float*)lens, (float*)out, B, C, H, W, H, W, B, 0, KB200_BILINEAR, KB200_ZEROS, 1,
-                            (cudaStream_t)stream);  // opt-in (KB200_REMAP_V2=1), declines otherwise
-    if (rc == KB200_EUNSUPPORTED) rc = undistort_tiled_forward((const float*)src, (const float*)lens, (float*)out, B, C, H, W, (cudaStream_t)stream);
+    rc = undistort_tiled_forward((const float*)src, (const float*)lens, (float*)out, B, C, H, W, (cudaStream_t)stream);
   }
   if (rc == KB200_EUNSUPPORTED) set_error("the fused undistort kernel covers fp32 images of 1 or 3 channels with a width divisible by 4");
   return rc;
@@ -506,12 +533,12 @@ int kb200_ssim_forward(const void* img1, const void* img2, const void* taps, voi
     set_error("the fused SSIM kernel is fp32 only");
     return KB200_EUNSUPPORTED;
   }
-  int rc = ssim_vwalk_forward((const float*)img1, (const float*)img2, (const float*)taps, (float*)out, planes, H, W, K, (float)C1,
-                              (float)C2, (float)eps, (cudaStream_t)stream);  // opt-in (KB200_SSIM_VWALK=1), declines otherwise
-  if (rc != KB200_EUNSUPPORTED) return rc;
-  rc = ssim_tiled_forward((const float*)img1, (const float*)img2, (const float*)taps, (float*)out, planes, H, W, K, (float)C1,
-                              (float)C2, (float)eps, (cudaStream_t)stream);
-  if (rc == KB200_EUNSUPPORTED) set_error("the fused SSIM kernel handles odd windows up to %d taps, got %d", SSIM_MAX_K, K);
+  KB_CHECK_ARG(K % 2 == 0 || K > SSIM_MAX_K || (K / 2 < H && K / 2 < W), "reflect border of %d needs an image larger than %d x %d", K / 2, H, W);
+  const int rc = ssim_vwalk_forward((const float*)img1, (const float*)img2, (const float*)taps, (float*)out, planes, H, W, K, (float)C1,
+                                    (float)C2, (float)eps, (cudaStream_t)stream);
+  if (rc == KB200_EUNSUPPORTED)
+    set_error("the fused SSIM kernel handles odd windows up to %d taps on rows that are a multiple of 4 floats (16-byte aligned), got K=%d W=%d",
+              SSIM_MAX_K, K, W);
   return rc;
 }
 

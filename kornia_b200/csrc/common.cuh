@@ -73,14 +73,39 @@ __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// cudaFuncSetAttribute is per device: remember, per kernel instantiation, on which devices it was applied
-inline bool first_use_on_device(unsigned long long& mask) {
-  int dev = 0;
+// ---------------------------------------------------------------- kernel-selection switches (capi.cu)
+// Which of the library's own kernels serves a request.  Every switch is read from the environment ONCE, when the library is
+// loaded (KB200_<NAME>=0|1), and can be changed afterwards through kb200_set_option (tests compare a tiled kernel with the
+// kernel it stands in for): no getenv on the call path.  -1 = automatic (the dispatcher's own rule).
+enum Option {
+  OPT_TMA,             // TMA-tiled warp / remap / backward kernels (off: the generic per-pixel kernels)
+  OPT_TILED_FILTER,    // shared-memory filter kernels (off: filter_generic.cuh)
+  OPT_SQUARE_TILES,    // second tile shape of the forward warp for rotated samples
+  OPT_SEP_VWALK,       // band-walking separable filter: -1 auto (13 taps and more), 0 never, 1 whenever it applies
+  OPT_TILED_GRADIENT,  // shared-memory derivative stencils (off: gradient.cuh)
+  OPT_U8_TILED,        // staged-window uint8 ingest warp (off: per-tap kernel)
+  OPT_BWD_V3,          // 4-pixel-unit tiled backward (off: warp_bwd_tma2)
+  OPT_COUNT
+};
+int option(Option o);
+
+// cudaFuncSetAttribute is per device: remember, per kernel instantiation, on which devices it was applied.  The bit is set
+// only AFTER the attribute call returned (see KB_SET_SMEM_ONCE), and atomically: two host threads driving different GPUs
+// (ctypes releases the GIL) may both apply the attribute, never launch without it.
+inline bool needs_attribute_on_device(const unsigned long long& mask, int& dev) {
+  dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return true;
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (mask & bit) return false;
-  mask |= bit;
-  return true;
+  return (__atomic_load_n(&mask, __ATOMIC_ACQUIRE) & (1ull << (dev & 63))) == 0;
 }
+inline void attribute_applied_on_device(unsigned long long& mask, int dev) { __atomic_fetch_or(&mask, 1ull << (dev & 63), __ATOMIC_RELEASE); }
+
+#define KB_SET_SMEM_ONCE(mask, kern, bytes)                                                                   \
+  do {                                                                                                       \
+    int dev__ = 0;                                                                                           \
+    if (::kb200::needs_attribute_on_device(mask, dev__)) {                                                   \
+      KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));        \
+      ::kb200::attribute_applied_on_device(mask, dev__);                                                     \
+    }                                                                                                        \
+  } while (0)
 
 }  // namespace kb200

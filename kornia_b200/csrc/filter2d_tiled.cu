@@ -9,9 +9,7 @@ static int launch_f2d_tiled(const CUtensorMap& map, const F2dTiledParams& p, cud
   constexpr size_t smem = (size_t)(2 * BH * SEPT_BW) * 4 + 2 * sizeof(uint64_t);
   auto kern = filter2d_tiled_kernel<K, BORDER, DOWN2>;
   static unsigned long long configured = 0;  // per instantiation, one bit per device
-  if (first_use_on_device(configured)) {
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  KB_SET_SMEM_ONCE(configured, kern, smem);
   const long long nstrips = (long long)p.planes * ceil_div(p.H, SEPT_TH);
   const long long cap = 3ll * sm_count();
   const int grid = (int)(nstrips < cap ? nstrips : cap);
@@ -53,8 +51,7 @@ int pyrdown_tiled_forward(const float* x, const float* k, float* out, int B, int
 // KB200_EUNSUPPORTED -> the caller runs filter2d_fwd_generic.
 int filter2d_tiled_forward(const float* x, const float* k, float* out, int B, int C, int H, int W, int Bk, int kh, int kw, int border,
                            int same, cudaStream_t st) {
-  const char* off = getenv("KB200_DISABLE_TILED_FILTER");
-  if (off && off[0] == '1') return KB200_EUNSUPPORTED;
+  if (!option(OPT_TILED_FILTER)) return KB200_EUNSUPPORTED;
   if (!same || kw != kh || (kw != 3 && kw != 5 && kw != 7) || border == KB200_CIRCULAR) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return KB200_EUNSUPPORTED;
   const int halo = (kw - 1) / 2;

@@ -9,9 +9,7 @@ static int launch_grad_tiled(const CUtensorMap& map, const GradTiledParams& p, c
   constexpr size_t smem = (size_t)(2 * BH * SEPT_BW) * 4 + 2 * sizeof(uint64_t);
   auto kern = grad_tiled_kernel<K, NOUT, MAG>;
   static unsigned long long configured = 0;  // per instantiation, one bit per device
-  if (first_use_on_device(configured)) {
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  KB_SET_SMEM_ONCE(configured, kern, smem);
   const long long nstrips = (long long)p.planes * ceil_div(p.H, SEPT_TH);
   const long long cap = 3ll * sm_count();
   const int grid = (int)(nstrips < cap ? nstrips : cap);
@@ -26,10 +24,7 @@ static int launch_grad_tiled(const CUtensorMap& map, const GradTiledParams& p, c
 
 int spatial_gradient_tiled_forward(const float* x, const double* taps, float* out, int planes, int H, int W, int nout, int k, int magnitude,
                                    double eps, cudaStream_t st) {
-  const char* on = getenv("KB200_TILED_GRADIENT");  // off by default: not yet run on hardware
-  if (!(on && on[0] == '1')) return KB200_EUNSUPPORTED;
-  const char* off = getenv("KB200_DISABLE_TILED_FILTER");
-  if (off && off[0] == '1') return KB200_EUNSUPPORTED;
+  if (!option(OPT_TILED_GRADIENT) || !option(OPT_TILED_FILTER)) return KB200_EUNSUPPORTED;
   if (!x || !out || !taps || (k != 3 && k != 5) || nout < 2 || nout > GRAD_MAX_OUT) return KB200_EUNSUPPORTED;
   if (magnitude && (nout != 2 || k != 3)) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return KB200_EUNSUPPORTED;

@@ -8,9 +8,7 @@ static int launch_remap_tiled(const CUtensorMap& map, const RemapTiledParams& p,
   auto kern = remap_tiled_kernel<NC, PAD, ALIGN, LENS>;
   constexpr size_t smem = (size_t)NC * 72 * 40 * 4 + 8 + 32 * 4 + 4 * 4 + 16;
   static unsigned long long configured = 0;  // per instantiation, one bit per device
-  if (first_use_on_device(configured)) {
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  KB_SET_SMEM_ONCE(configured, kern, smem);
   const dim3 grid(ceil_div(p.w, 64), ceil_div(p.h, 32), p.B);
   kern<<<grid, 256, smem, st>>>(map, p);
   cudaError_t e = cudaGetLastError();
@@ -24,8 +22,7 @@ static int launch_remap_tiled(const CUtensorMap& map, const RemapTiledParams& p,
 // KB200_EUNSUPPORTED -> the caller runs the generic kernel.
 int remap_tiled_forward(const float* src, const float* map_x, const float* map_y, float* out, int B, int C, int H, int W, int h, int w,
                         int Bmap, int normalized, int interp, int pad, int align, cudaStream_t st) {
-  const char* off = getenv("KB200_DISABLE_TMA");
-  if (off && off[0] == '1') return KB200_EUNSUPPORTED;
+  if (!option(OPT_TMA)) return KB200_EUNSUPPORTED;
   if (interp != KB200_BILINEAR || (C != 1 && C != 3) || pad == KB200_FILL) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || B > 65535 || ceil_div(h, 32) > 65535) return KB200_EUNSUPPORTED;
   EncodeTiledFn encode = encode_tiled_fn();

@@ -228,8 +228,5 @@ int remap_tiled_forward(const float* src, const float* map_x, const float* map_y
                         int Bmap, int normalized, int interp, int pad, int align, cudaStream_t st);
 // undistort_image in one kernel: bilinear, zeros, align_corners=True, output size = input size; lens (B,16).
 int undistort_tiled_forward(const float* src, const float* lens, float* out, int B, int C, int H, int W, cudaStream_t st);
-// Warp-pipelined persistent variant of both (remap_warp.cuh), opt-in with KB200_REMAP_V2=1; lens != nullptr selects the fused undistort.
-int remap_warp_forward(const float* src, const float* map_x, const float* map_y, const float* lens, float* out, int B, int C, int H, int W, int h,
-                       int w, int Bmap, int normalized, int interp, int pad, int align, cudaStream_t st);
 
 }  // namespace kb200

@@ -9,9 +9,7 @@ static int launch_sep_tiled(const CUtensorMap& map, const SepTiledParams& p, cud
   constexpr size_t smem = (size_t)(2 * BH * SEPT_BW + BH * SEPT_TW) * 4 + 2 * sizeof(uint64_t);
   auto kern = sepfilter_tiled_kernel<K, BORDER, LERP>;
   static unsigned long long configured = 0;  // per instantiation, one bit per device
-  if (first_use_on_device(configured)) {
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  KB_SET_SMEM_ONCE(configured, kern, smem);
   const long long nstrips = (long long)p.planes * ceil_div(p.H, SEPT_TH);
   const long long cap = 3ll * sm_count();
   const int grid = (int)(nstrips < cap ? nstrips : cap);
@@ -28,8 +26,7 @@ static int launch_sep_tiled(const CUtensorMap& map, const SepTiledParams& p, cud
 // > 17-tap kernels, rows not 16-byte aligned, images narrower than the fold distance).
 int sepfilter_tiled_forward(const float* x, const float* kx, const float* ky, float* out, int B, int C, int H, int W,
                                    int Bkx, int kw, int Bky, int kh, int border, int same, cudaStream_t st, const float* lerp_w) {
-  const char* off = getenv("KB200_DISABLE_TILED_FILTER");
-  if (off && off[0] == '1') return KB200_EUNSUPPORTED;
+  if (!option(OPT_TILED_FILTER)) return KB200_EUNSUPPORTED;
   if (!same || kw != kh || (kw & 1) == 0 || kw < 3 || kw > 17 || border == KB200_CIRCULAR) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 7) != 0) return KB200_EUNSUPPORTED;
   const int halo = (kw - 1) / 2;

@@ -3,24 +3,14 @@
 
 namespace kb200 {
 
-// Experiment knob for the persistent opt-in kernels: resident CTAs per SM the grid is sized for (default: the kernel's
-// launch bounds).  KB200_GRID_PER_SM=1|2|3 -- a smaller grid means fewer, longer-running CTAs (less L2 / TMA contention).
-static inline long long grid_per_sm(long long dflt) {
-  const char* e = getenv("KB200_GRID_PER_SM");
-  const int v = e ? atoi(e) : 0;
-  return (v >= 1 && v <= dflt) ? v : dflt;
-}
-
 template <int K, int BORDER, bool LERP = false>
 static int launch_sep_vwalk(const CUtensorMap& map_main, const CUtensorMap& map_pro, const SepTiledParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)(2 * SEPT_TH * SEPT_BW + (SEPT_TH + K - 1) * SEPT_TW) * 4 + 2 * sizeof(uint64_t);
   auto kern = sepfilter_vwalk_kernel<K, BORDER, LERP>;
   static unsigned long long configured = 0;  // per instantiation, one bit per device
-  if (first_use_on_device(configured)) {
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  KB_SET_SMEM_ONCE(configured, kern, smem);
   const long long nbands = (long long)p.planes * ceil_div(p.W, SEPT_TW);
-  const long long cap = grid_per_sm(3) * sm_count();
+  const long long cap = 3ll * sm_count();
   const int grid = (int)(nbands < cap ? nbands : cap);
   kern<<<grid, 256, smem, st>>>(map_main, map_pro, p);
   cudaError_t e = cudaGetLastError();
@@ -33,10 +23,10 @@ static int launch_sep_vwalk(const CUtensorMap& map_main, const CUtensorMap& map_
 
 int sepfilter_vwalk_forward(const float* x, const float* kx, const float* ky, float* out, int B, int C, int H, int W, int Bkx, int kw,
                             int Bky, int kh, int border, int same, cudaStream_t st, const float* lerp_w) {
-  const char* on = getenv("KB200_SEP_VWALK");  // off by default: not yet run on hardware
-  if (!(on && on[0] == '1')) return KB200_EUNSUPPORTED;
-  const char* off = getenv("KB200_DISABLE_TILED_FILTER");  // tests use it to reach the generic kernel
-  if (off && off[0] == '1') return KB200_EUNSUPPORTED;
+  // Measured on B200 (profiles/r2_variants_B64.txt): the band walk wins from 13 taps up (17 taps: 0.96 -> 0.70 ms at B=64) and
+  // loses below (5 taps: 0.56 -> 0.60 ms; the lerp epilogue of unsharp_mask 0.69 -> 0.86 ms), so that is the automatic rule.
+  const int sel = option(OPT_SEP_VWALK);
+  if (sel == 0 || (sel < 0 && (kw < 13 || lerp_w)) || !option(OPT_TILED_FILTER)) return KB200_EUNSUPPORTED;
   if (!same || kw != kh || (kw & 1) == 0 || kw < 3 || kw > 17 || border == KB200_CIRCULAR) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 7) != 0) return KB200_EUNSUPPORTED;
   const int halo = (kw - 1) / 2;

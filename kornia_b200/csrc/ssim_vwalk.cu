@@ -3,22 +3,12 @@
 
 namespace kb200 {
 
-// Experiment knob for the persistent opt-in kernels: resident CTAs per SM the grid is sized for (default: the kernel's
-// launch bounds).  KB200_GRID_PER_SM=1|2|3 -- a smaller grid means fewer, longer-running CTAs (less L2 / TMA contention).
-static inline long long grid_per_sm(long long dflt) {
-  const char* e = getenv("KB200_GRID_PER_SM");
-  const int v = e ? atoi(e) : 0;
-  return (v >= 1 && v <= dflt) ? v : dflt;
-}
-
 template <int K>
 static int launch_ssimv(const CUtensorMap maps[4], const SsimVParams& p, cudaStream_t st) {
   auto kern = ssim_vwalk_kernel<K>;
   static unsigned long long configured = 0;
-  if (first_use_on_device(configured))
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssimv_smem_bytes<K>()));
-  const long long nbands = (long long)p.planes * ceil_div(p.W, SSIMV_TW);
-  const long long cap = grid_per_sm(2) * sm_count();
+  KB_SET_SMEM_ONCE(configured, kern, ssimv_smem_bytes<K>());const long long nbands = (long long)p.planes * ceil_div(p.W, SSIMV_TW);
+  const long long cap = 2ll * sm_count();
   const int grid = (int)(nbands < cap ? nbands : cap);
   kern<<<grid, 256, ssimv_smem_bytes<K>(), st>>>(maps[0], maps[1], maps[2], maps[3], p);
   cudaError_t e = cudaGetLastError();
@@ -31,8 +21,6 @@ static int launch_ssimv(const CUtensorMap maps[4], const SsimVParams& p, cudaStr
 
 int ssim_vwalk_forward(const float* a, const float* b, const float* taps, float* out, int planes, int H, int W, int K, float C1, float C2,
                        float eps, cudaStream_t st) {
-  const char* on = getenv("KB200_SSIM_VWALK");  // off by default: not yet run on hardware
-  if (!(on && on[0] == '1')) return KB200_EUNSUPPORTED;
   if (K % 2 == 0 || K < 3 || K > SSIM_MAX_K || K / 2 >= H || K / 2 >= W) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(a) & 15) != 0 || (reinterpret_cast<uintptr_t>(b) & 15) != 0 ||
       (reinterpret_cast<uintptr_t>(out) & 7) != 0)

@@ -18,9 +18,11 @@
 // ssim_tiled_kernel.
 #pragma once
 #include "sepfilter_tiled.cuh"
-#include "ssim_tiled.cuh"
+#include "filter_generic.cuh"
 
 namespace kb200 {
+
+constexpr int SSIM_MAX_K = 11;  // odd Gaussian windows up to 11 taps (the reference's default window)
 
 constexpr int SSIMV_TW = 64;
 constexpr int SSIMV_TH = 32;
@@ -268,5 +270,10 @@ __global__ void __launch_bounds__(256, 2) ssim_vwalk_kernel(const __grid_constan
     }
   }
 }
+
+// host entry (ssim_vwalk.cu).  KB200_EUNSUPPORTED outside the kernel's envelope (even / > 11-tap windows, rows that are not a
+// multiple of 4 floats): the Python layer then composes five one-pass blurs and torch elementwise ops.
+int ssim_vwalk_forward(const float* a, const float* b, const float* taps, float* out, int planes, int H, int W, int K, float C1, float C2,
+                       float eps, cudaStream_t st);
 
 }  // namespace kb200

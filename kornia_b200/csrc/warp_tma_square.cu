@@ -13,10 +13,10 @@ constexpr int SQ_TW = 32, SQ_TH = 32, SQ_BW = 56, SQ_BH = 56, SQ_STAGES = 2, SQ_
 template <int NC, int PAD>
 static int launch_square(const CUtensorMap& map, const TmaWarpParams& p, bool projective, bool align, cudaStream_t st) {
   if (projective)
-    return align ? launch_warp_tma_cfg<NC, KB200_BILINEAR, PAD, true, true, SQ_TW, SQ_TH, SQ_BW, SQ_BH, SQ_STAGES>(map, p, SQ_CTAS, st)
-                 : launch_warp_tma_cfg<NC, KB200_BILINEAR, PAD, true, false, SQ_TW, SQ_TH, SQ_BW, SQ_BH, SQ_STAGES>(map, p, SQ_CTAS, st);
-  return align ? launch_warp_tma_cfg<NC, KB200_BILINEAR, PAD, false, true, SQ_TW, SQ_TH, SQ_BW, SQ_BH, SQ_STAGES>(map, p, SQ_CTAS, st)
-               : launch_warp_tma_cfg<NC, KB200_BILINEAR, PAD, false, false, SQ_TW, SQ_TH, SQ_BW, SQ_BH, SQ_STAGES>(map, p, SQ_CTAS, st);
+    return align ? launch_warp_tma<NC, KB200_BILINEAR, PAD, true, true, SQ_TW, SQ_TH, SQ_BW, SQ_BH, SQ_STAGES>(map, p, st, SQ_CTAS)
+                 : launch_warp_tma<NC, KB200_BILINEAR, PAD, true, false, SQ_TW, SQ_TH, SQ_BW, SQ_BH, SQ_STAGES>(map, p, st, SQ_CTAS);
+  return align ? launch_warp_tma<NC, KB200_BILINEAR, PAD, false, true, SQ_TW, SQ_TH, SQ_BW, SQ_BH, SQ_STAGES>(map, p, st, SQ_CTAS)
+               : launch_warp_tma<NC, KB200_BILINEAR, PAD, false, false, SQ_TW, SQ_TH, SQ_BW, SQ_BH, SQ_STAGES>(map, p, st, SQ_CTAS);
 }
 
 int warp_tma_forward_square(const TmaFwdArgs& a, cudaStream_t st) {
@@ -32,7 +32,7 @@ int warp_tma_forward_square(const TmaFwdArgs& a, cudaStream_t st) {
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return KB200_EUNSUPPORTED;
-  const TmaWarpParams p{a.src, a.m, a.bx, a.by, a.fill, a.out, a.B, a.H, a.W, a.h, a.w, a.Bm, a.align, 0, a.only_class};
+  const TmaWarpParams p{a.src, a.m, a.bx, a.by, a.fill, a.out, a.B, a.H, a.W, a.h, a.w, a.Bm, a.align, a.only_class};
   const bool projective = a.projective != 0, align = a.align != 0;
 #define KB_SQ_CASE(NC_, PAD_) \
   if (a.C == NC_ && a.pad == PAD_) return launch_square<NC_, PAD_>(map, p, projective, align, st);

@@ -47,8 +47,7 @@ static int launch_u8_tiled(const WarpU8Params& p, cudaStream_t st) {
 
 // KB200_EUNSUPPORTED: the request is served by warp_fwd_u8hwc instead.
 static int u8_tiled_forward(const WarpU8Params& p, int projective, int interp, int pad, cudaStream_t st) {
-  const char* simple = getenv("KB200_U8_SIMPLE");
-  if (simple && simple[0] == '1') return KB200_EUNSUPPORTED;
+  if (!option(OPT_U8_TILED)) return KB200_EUNSUPPORTED;
   if (interp != KB200_BILINEAR || (p.C != 1 && p.C != 3 && p.C != 4)) return KB200_EUNSUPPORTED;
   // aligned 32-bit loads of whole in-image groups of 4 pixels: every image row starts on a 4-byte boundary
   if (p.W % 4 != 0 || (reinterpret_cast<uintptr_t>(p.src) & 3) != 0) return KB200_EUNSUPPORTED;

@@ -98,16 +98,16 @@ FUSED_MIN_BATCH = 2     # below this torch's bmm takes a different (gemv-like) p
 
 
 def torch_prelude_forced() -> bool:
-    import os
+    from .. import config
 
-    return os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") == "1"
+    return config.enabled("torch_prelude")
 
 
 def sampling_matrix(M: torch.Tensor, src_hw, dst_hw, affine: bool) -> torch.Tensor:
     """inverse(normalize_homography(M3)) -- the (B,3,3) dst-normalised -> src-normalised map the kernels
     consume.  One CUDA launch (and one more for its backward) when M is a CUDA fp32/fp64 tensor with batch >= 2;
-    the reference's torch op sequence otherwise or when KORNIA_B200_TORCH_PRELUDE=1.  The fused backward has no
-    autograd formula of its own: double backward through M needs KORNIA_B200_TORCH_PRELUDE=1."""
+    the reference's torch op sequence otherwise or when ``config.set("torch_prelude", 1)`` (KB200_TORCH_PRELUDE=1).  The fused
+    backward has no autograd formula of its own: double backward through M needs that switch."""
     from .. import _ops
 
     fused_ok = (M.is_cuda and M.dtype in (torch.float32, torch.float64) and M.shape[0] >= FUSED_MIN_BATCH and not torch_prelude_forced())

@@ -1,17 +1,15 @@
 """Drop-in ``undistort_image`` (reference: kornia/geometry/calibration/undistort.py:138-198):
 every output pixel is pushed through the lens model (``distort_points``) to find where the distorted image holds
 it, and the image is resampled there by ``remap`` -- the tiled TMA kernel of csrc/remap_tiled.cuh (bilinear,
-zeros, align_corners=True).  By default the maps are (B,H,W) torch tensors as in the reference.  The one-kernel form
-(kb200_undistort_forward: the lens model evaluated per pixel in registers, no maps, ~45 fewer elementwise passes) is
-written and passes on the host emulator but has not run on hardware yet: opt-in with KB200_FUSED_UNDISTORT=1 (DESIGN.md
-section 9)."""
+zeros, align_corners=True).  When no gradient is needed and the tilt coefficients are zero, the one-kernel form runs instead
+(kb200_undistort_forward: the lens model evaluated per pixel in registers, no maps, ~45 fewer elementwise passes):
+bit-identical to maps + remap on the same device and 17x faster on a B200 (profiles/r2_variants_B64.txt);
+``config.set("fused_undistort", 0)`` selects the composition."""
 from __future__ import annotations
-
-import os
 
 import torch
 
-from ... import _lib, _ops
+from ... import _lib, _ops, config
 from ..transform.imgwarp import remap
 from .distort import distort_points
 
@@ -21,9 +19,9 @@ __all__ = ["undistort_image", "undistort_image_from_uint8"]
 def _fused_request(image: torch.Tensor, K: torch.Tensor, dist: torch.Tensor, B: int):
     """(B,16) lens numbers fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, k5, k6, s1..s4 when the one-kernel path
     (kb200_undistort_forward: the lens model evaluated per pixel inside the sampling kernel, no maps) may serve the call,
-    else None.  Off unless KB200_FUSED_UNDISTORT=1: written after the round's GPU budget was spent, not yet run on
-    hardware.  Not taken when a gradient is needed or the tilt coefficients are set."""
-    if os.environ.get("KB200_FUSED_UNDISTORT") != "1":
+    else None (switch ``fused_undistort`` of kornia_b200.config, on by default).  Not taken when a gradient is needed or the
+    tilt coefficients are set."""
+    if not config.enabled("fused_undistort") or torch.compiler.is_compiling():
         return None
     if not (image.is_cuda and image.dtype == torch.float32):
         return None

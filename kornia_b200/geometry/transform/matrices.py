@@ -33,14 +33,12 @@ def _eye3(like: torch.Tensor) -> torch.Tensor:
 def _fused_ok(*tensors: torch.Tensor) -> bool:
     """One-launch builders apply to CUDA fp32/fp64 inputs with batch >= 2 that need no gradient (torch's batched GEMM
     takes another path for a single sample; autograd keeps the torch op sequence)."""
-    import os
-
-    from .._prelude import FUSED_MIN_BATCH
+    from .._prelude import FUSED_MIN_BATCH, torch_prelude_forced
 
     t0 = tensors[0]
     return (all(t.is_cuda for t in tensors) and t0.dtype in (torch.float32, torch.float64) and t0.shape[0] >= FUSED_MIN_BATCH
             and not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors))
-            and os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") != "1")
+            and not torch_prelude_forced())
 
 
 def _fused_rotation(center: torch.Tensor, angle: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
@@ -129,17 +127,15 @@ def get_perspective_transform(points_src: torch.Tensor, points_dst: torch.Tensor
     """(B,3,3) homography taking the four ``points_src`` (B,4,2; x,y) onto ``points_dst``, scaled so
     that H[2,2] = 1: H = Q(dst) @ Q(src)^-1 with Q the unit-square-to-quad map (imgwarp.py:444-527).
     CUDA fp32/fp64 points with batch >= 2 take one fused launch; anything else (CPU points, half
-    precision, a single sample, KORNIA_B200_TORCH_PRELUDE=1) the reference's torch op sequence."""
-    import os
-
-    from .._prelude import FUSED_MIN_BATCH
+    precision, a single sample, the ``torch_prelude`` switch of kornia_b200.config) the reference's torch op sequence."""
+    from .._prelude import FUSED_MIN_BATCH, torch_prelude_forced
 
     check_shape(points_src, ["B", "4", "2"])
     check_shape(points_dst, ["B", "4", "2"])
     check(points_src.shape == points_dst.shape, "Source data shape must match Destination data shape.")
     check(points_src.dtype == points_dst.dtype, "Source data type must match Destination data type.")
     fused_ok = (points_src.is_cuda and points_dst.is_cuda and points_src.dtype in (torch.float32, torch.float64)
-                and points_src.shape[0] >= FUSED_MIN_BATCH and os.environ.get("KORNIA_B200_TORCH_PRELUDE", "0") != "1")
+                and points_src.shape[0] >= FUSED_MIN_BATCH and not torch_prelude_forced())
     if fused_ok:
         needs_grad = torch.is_grad_enabled() and (points_src.requires_grad or points_dst.requires_grad)
         if not needs_grad:

@@ -5,19 +5,17 @@ The blur is the 5x5 binomial stencil through :func:`kornia_b200.filters.filter2d
 kernel of csrc/filter2d_tiled.cuh (border folded into the tile load, no ``F.pad`` copy).  The 2x
 resampling step is ``torch.nn.functional.interpolate``, the third-party call the reference itself makes
 at pyramid.py:450-455,496-498 (the reference's own ``TODO: use kornia.geometry.resize``): 5 B/element of
-traffic next to the blur's 8, left to ATen by default.  At an exact factor of two the resampling is a 2x2 average and
-runs in the blur kernel's epilogue (kb200_pyrdown_forward): written, passes on the host emulator, not yet run on
-hardware, opt-in with KB200_FUSED_PYRDOWN=1.  ``ScalePyramid`` (the SIFT octave builder) is a feature-
+traffic next to the blur's 8.  At an exact factor of two (``align_corners=False``, no gradient) the resampling is a 2x2
+average and runs in the blur kernel's epilogue (kb200_pyrdown_forward): bit-identical to the composition and 2.2x faster on
+a B200 (profiles/r2_variants_B64.txt); ``config.set("fused_pyrdown", 0)`` selects the composition.  ``ScalePyramid`` (the SIFT octave builder) is a feature-
 detection caller and stays out of scope."""
 from __future__ import annotations
-
-import os
 
 import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ... import _lib, _ops
+from ... import _lib, _ops, config
 from ...core.check import check, check_shape
 from ...filters.filter import filter2d
 
@@ -36,9 +34,8 @@ def _binomial5x5() -> torch.Tensor:
 def _fused_request(input: torch.Tensor, border_type: str, align_corners: bool, factor: float):
     """(taps, border code) when the one-pass kernel (kb200_pyrdown_forward: the 2x2 average that the bilinear
     resampling reduces to at an exact factor of two runs in the blur's epilogue) may serve the call, else None.
-    Off unless KB200_FUSED_PYRDOWN=1: the kernel was written after the round's GPU budget was spent and has not run
-    on hardware yet."""
-    if os.environ.get("KB200_FUSED_PYRDOWN") != "1":
+    Switch ``fused_pyrdown`` of kornia_b200.config (on by default)."""
+    if not config.enabled("fused_pyrdown") or torch.compiler.is_compiling():
         return None
     if not (input.is_cuda and input.dtype == torch.float32) or (torch.is_grad_enabled() and input.requires_grad):
         return None

@@ -54,3 +54,12 @@ def golden(name):
     if name not in _CACHE:
         _CACHE[name] = Golden(name)
     return _CACHE[name]
+
+
+@pytest.fixture(autouse=True)
+def _default_kernel_switches():
+    """Tests flip kernel-selection switches (kornia_b200.config); every test starts from, and leaves, the defaults."""
+    yield
+    mod = sys.modules.get("kornia_b200.config")
+    if mod is not None:
+        mod.reset()

@@ -163,10 +163,10 @@ def test_fused_perspective_from_points_matches_torch_ops(dtype, monkeypatch):
     before = K._ops.launch_count
     fused = KT.get_perspective_transform(src, dst)
     assert K._ops.launch_count == before + 1
-    monkeypatch.setenv("KORNIA_B200_TORCH_PRELUDE", "1")
+    K.config.set("torch_prelude", 1)
     plain = KT.get_perspective_transform(src, dst)
     assert K._ops.launch_count == before + 1
-    monkeypatch.delenv("KORNIA_B200_TORCH_PRELUDE")
+    K.config.set("torch_prelude", 0)
     tol = dict(rtol=2e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-12, atol=1e-13)
     torch.testing.assert_close(fused, plain, **tol)
     torch.testing.assert_close(fused.cpu(), R.perspective_from_points(src.cpu(), dst.cpu()), rtol=1e-4, atol=1e-5)
@@ -175,7 +175,7 @@ def test_fused_perspective_from_points_matches_torch_ops(dtype, monkeypatch):
     a, b = src.clone().requires_grad_(True), dst.clone().requires_grad_(True)
     cot = torch.rand(64, 3, 3, device=DEV, dtype=dtype)
     ga, gb = torch.autograd.grad((KT.get_perspective_transform(a, b) * cot).sum(), [a, b])
-    monkeypatch.setenv("KORNIA_B200_TORCH_PRELUDE", "1")
+    K.config.set("torch_prelude", 1)
     a2, b2 = src.clone().requires_grad_(True), dst.clone().requires_grad_(True)
     ga2, gb2 = torch.autograd.grad((KT.get_perspective_transform(a2, b2) * cot).sum(), [a2, b2])
     assert rel_l2(ga, ga2) < 1e-5 and rel_l2(gb, gb2) < 1e-5
@@ -201,10 +201,10 @@ def test_fused_rotation_matrix_matches_torch_ops(dtype, monkeypatch):
     before = K._ops.launch_count
     fused = KT.get_rotation_matrix2d(center, angle, scale)
     assert K._ops.launch_count == before + 1 and fused.shape == (64, 2, 3)
-    monkeypatch.setenv("KORNIA_B200_TORCH_PRELUDE", "1")
+    K.config.set("torch_prelude", 1)
     plain = KT.get_rotation_matrix2d(center, angle, scale)
     assert K._ops.launch_count == before + 1
-    monkeypatch.delenv("KORNIA_B200_TORCH_PRELUDE")
+    K.config.set("torch_prelude", 0)
     tol = dict(rtol=1e-5, atol=2e-4) if dtype == torch.float32 else dict(rtol=1e-12, atol=1e-10)  # translations reach ~1e3
     torch.testing.assert_close(fused, plain, **tol)
     torch.testing.assert_close(fused.cpu(), R.rotation_matrix2d(center.cpu(), angle.cpu(), scale.cpu()), rtol=1e-4, atol=1e-3)
@@ -216,7 +216,7 @@ def test_fused_rotation_matrix_matches_torch_ops(dtype, monkeypatch):
     img = torch.rand(8, 3, 96, 128, device=DEV, dtype=dtype)
     ang8 = angle[:8]
     fused_img = KT.rotate(img, ang8)
-    monkeypatch.setenv("KORNIA_B200_TORCH_PRELUDE", "1")
+    K.config.set("torch_prelude", 1)
     torch.testing.assert_close(fused_img, KT.rotate(img, ang8), rtol=1e-4, atol=1e-5)
 
 

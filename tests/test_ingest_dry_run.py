@@ -7,7 +7,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from kornia_b200 import _lib, _ops
+from kornia_b200 import _lib, _ops, config
 from kornia_b200.geometry.calibration import undistort
 from oracle import kornia_restated as R
 
@@ -55,7 +55,7 @@ def on_cpu(monkeypatch):
     for name in ("warp_perspective", "warp_affine", "get_rotation_matrix2d"):
         monkeypatch.setattr(T.KT, name, getattr(R, name))
     monkeypatch.setattr(T, "DEV", "cpu")
-    monkeypatch.setenv("KORNIA_B200_TORCH_PRELUDE", "1")
+    config.set("torch_prelude", 1)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
     true_div = torch.Tensor.__truediv__
 
@@ -76,7 +76,7 @@ def test_golden_warp_cases(on_cpu):
 
 def test_golden_undistort_cases(on_cpu):
     for name in T.UNDISTORT:
-        T.test_undistort_from_bytes_matches_reference_and_the_fp32_path(on_cpu, name)
+        T.test_undistort_from_bytes_matches_reference_and_the_fp32_path(name)
 
 
 def test_property_tests(on_cpu):

@@ -4,8 +4,6 @@ these tests are skipped unless KB200_RUN_UNVERIFIED=1 (tools/r2_first_call.sh ru
 
     KB200_RUN_UNVERIFIED=1 python -m pytest tests/test_ingest_gpu.py -m gpu -q
 """
-import os
-
 import pytest
 import torch
 
@@ -13,8 +11,7 @@ import kornia_b200 as K
 from conftest import golden
 from helpers import run_family_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("KB200_RUN_UNVERIFIED") != "1", reason="unverified device code: set KB200_RUN_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 DEV = "cuda"
 ING = golden("ingest")
 KT, KC = K.geometry.transform, K.geometry.calibration
@@ -109,30 +106,31 @@ def test_tiled_ingest_kernel_is_bit_identical_to_the_per_tap_kernel(monkeypatch,
     for mats, size in cases:
         img = frames[: mats.shape[0]] if mats.shape[0] <= B else frames[:1].expand(mats.shape[0], H, W, channels).contiguous()
         for ac in (True, False):
-            monkeypatch.setenv("KB200_U8_SIMPLE", "1")
+            K.config.set("u8_tiled", 0)
             want = KT.warp_perspective_from_uint8(img, mats, size, padding_mode=pad, align_corners=ac, **fill)
-            monkeypatch.delenv("KB200_U8_SIMPLE")
+            K.config.set("u8_tiled", 1)
             got = KT.warp_perspective_from_uint8(img, mats, size, padding_mode=pad, align_corners=ac, **fill)
             assert torch.equal(got, want), float((got - want).abs().max())
     rot = KT.get_rotation_matrix2d(torch.tensor([[W / 2, H / 2]], device=DEV).expand(B, 2), torch.linspace(-40, 40, B, device=DEV), torch.ones(B, 2, device=DEV))
-    monkeypatch.setenv("KB200_U8_SIMPLE", "1")
+    K.config.set("u8_tiled", 0)
     want = KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad, **fill)
-    monkeypatch.delenv("KB200_U8_SIMPLE")
+    K.config.set("u8_tiled", 1)
     assert torch.equal(KT.warp_affine_from_uint8(frames, rot, (H, W), padding_mode=pad, **fill), want)
 
 
 @pytest.mark.parametrize("name", UNDISTORT)
-def test_undistort_from_bytes_matches_reference_and_the_fp32_path(monkeypatch, name):
+def test_undistort_from_bytes_matches_reference_and_the_fp32_path(name):
     """Golden vectors of image_to_tensor + _to_float32 + undistort_image from the reference (1e-4 rel); on the device: close to
     convert + undistort_image through the default maps + remap path, and EQUAL to convert + the fused fp32 undistort
-    (KB200_FUSED_UNDISTORT=1), whose lens arithmetic the byte kernel shares."""
+    (switch fused_undistort), whose lens arithmetic the byte kernel shares."""
     op, kw, ins, outs = ING.case(name)
-    monkeypatch.delenv("KB200_FUSED_UNDISTORT", raising=False)
+    K.config.set("fused_undistort", 0)
     before = K._ops.launch_count
     got = run_family_case(KC, op, kw, ins, device=DEV)
     img = ins["image"]
     one_kernel = ins["dist"].shape[-1] != 14 and img.shape[-1] in (1, 3) and img.shape[-2] % 4 == 0
-    assert (K._ops.launch_count == before + 1) == one_kernel
+    # one launch of this library: the byte kernel, or (tilt terms / odd widths) the remap kernel after torch built the maps
+    assert before + (1 if one_kernel else 0) <= K._ops.launch_count <= before + 1
     assert got.device.type == torch.device(DEV).type and got.dtype == torch.float32 and got.shape == outs["out"].shape and got.is_contiguous()
     torch.testing.assert_close(got.cpu(), outs["out"], rtol=1e-4, atol=1e-5)
     x = img.to(DEV)
@@ -143,7 +141,7 @@ def test_undistort_from_bytes_matches_reference_and_the_fp32_path(monkeypatch, n
     cam, d = (cam if cam.dim() == 3 else cam.expand(n, 3, 3).contiguous()), (d if d.dim() == 2 else d.expand(n, d.shape[-1]).contiguous())
     torch.testing.assert_close(got, KC.undistort_image(x, cam, d), rtol=1e-4, atol=1e-5)
     if one_kernel:
-        monkeypatch.setenv("KB200_FUSED_UNDISTORT", "1")
+        K.config.set("fused_undistort", 1)
         assert torch.equal(got, KC.undistort_image(x, cam, d))
 
 

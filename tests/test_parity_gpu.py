@@ -178,17 +178,12 @@ def _bench_homographies(B, H, W, seed, sigma=8.0):
 
 def _generic(fn, check_variant=True):
     """Run ``fn`` with the tiled kernels disabled (the C ABI then dispatches the generic kernels)."""
-    import os
-
     from kornia_b200 import _lib
 
-    os.environ["KB200_DISABLE_TMA"] = "1"
-    try:
+    with K.config.override(tma=0):
         out = fn()
         if check_variant:  # only kb200_warp_forward records the variant it dispatched to
             assert _lib.last_warp_variant() == "generic"
-    finally:
-        del os.environ["KB200_DISABLE_TMA"]
     return out
 
 
@@ -351,11 +346,8 @@ def test_tiled_sepfilter_bit_identical_to_generic(k, border):
         kx = torch.randn(B, k, generator=g).to(DEV)
         ky = torch.randn(1, k, generator=g).to(DEV)
         a = K.filter2d_separable(x, kx, ky, border)
-        os.environ["KB200_DISABLE_TILED_FILTER"] = "1"
-        try:
+        with K.config.override(tiled_filter=0):
             b = K.filter2d_separable(x, kx, ky, border)
-        finally:
-            del os.environ["KB200_DISABLE_TILED_FILTER"]
         assert torch.equal(a, b), (B, C, H, W, float((a - b).abs().max()))
         want = R.filter2d_separable(x.cpu(), kx.cpu(), ky.cpu(), border)
         torch.testing.assert_close(a.cpu(), want, rtol=1e-4, atol=1e-5)
@@ -454,11 +446,8 @@ def test_tiled_filter2d_bit_identical_to_generic(k, border):
             kern = kern.to(DEV)
             for normalized, behaviour in ((False, "corr"), (True, "conv")):
                 a = K.filter2d(x, kern, border, normalized=normalized, behaviour=behaviour)
-                os.environ["KB200_DISABLE_TILED_FILTER"] = "1"
-                try:
+                with K.config.override(tiled_filter=0):
                     b = K.filter2d(x, kern, border, normalized=normalized, behaviour=behaviour)
-                finally:
-                    del os.environ["KB200_DISABLE_TILED_FILTER"]
                 assert torch.equal(a, b), (B, C, H, W, float((a - b).abs().max()))
                 want = R.filter2d(x.cpu(), kern.cpu(), border, normalized=normalized, behaviour=behaviour)
                 torch.testing.assert_close(a.cpu(), want, rtol=1e-4, atol=1e-5)

@@ -2,7 +2,6 @@
 samples on 32x32 tiles with a 56x56 box.  Every sample must be written exactly once and the result must equal, bit
 for bit, the single-kernel tiled path and the generic kernel."""
 import math
-import os
 
 import pytest
 import torch
@@ -30,11 +29,10 @@ def _forward_into_nan(src, M, dsize, projective, pad, align, fill=None):
 
 
 def _with_env(name, fn):
-    os.environ[name] = "1"
-    try:
+    """Run ``fn`` with one kernel family switched off (kornia_b200.config)."""
+    option = {"KB200_DISABLE_SQUARE_TILES": "square_tiles", "KB200_DISABLE_TMA": "tma"}[name]
+    with K.config.override(**{option: 0}):
         return fn()
-    finally:
-        del os.environ[name]
 
 
 def _mixed_affines(B, H, W):

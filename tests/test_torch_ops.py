@@ -144,7 +144,9 @@ def test_opcheck_caller_operators():
     from torch.library import opcheck
 
     src, M = _inputs()
-    taps, nout, k = K.filters.sobel._host_taps("sobel", 1, True, torch.float32)
+    import importlib
+
+    taps, nout, k = importlib.import_module("kornia_b200.filters.sobel")._host_taps("sobel", 1, True, torch.float32)
     opcheck(ops.spatial_gradient_fwd, (src.clone().requires_grad_(True), list(taps), nout, k, False, 0.0))
     opcheck(ops.spatial_gradient_fwd, (src, list(taps), nout, k, True, 1e-6), test_utils=("test_schema", "test_faketensor"))
     kern = K.filters.get_gaussian_kernel1d(7, 1.5, device="cuda")
@@ -192,8 +194,9 @@ def test_torch_compile_fullgraph_matches_eager(backend):
             pytest.skip(f"inductor unavailable here: {type(e).__name__}: {str(e)[:200]}")
         raise
     # the kernels are the same launches in both modes (bit-identical); the torch glue around them may fuse differently
-    for g, w in zip(got, want):
-        torch.testing.assert_close(g, w, rtol=1e-5, atol=1e-5)
+    # (d/dM are sums over ~1500 pixels of terms of both signs: the fused glue moves their last bits)
+    for g, w, tol in zip(got, want, (1e-5, 1e-5, 2e-4)):
+        torch.testing.assert_close(g, w, rtol=tol, atol=tol * max(1.0, float(w.abs().max())))
 
 
 @gpu

@@ -18,7 +18,7 @@ for k in (3, 5, 7):
     kern = torch.randn(1, k, k, device=dev)
     f = lambda: K.filter2d(x, kern)
     a = t(f)
-    os.environ["KB200_DISABLE_TILED_FILTER"] = "1"; b = t(f, 3); del os.environ["KB200_DISABLE_TILED_FILTER"]
+    K.config.set("tiled_filter", 0); b = t(f, 3); K.config.reset()
     gbs = 24.0 * B * 1080 * 1920 / a / 1e6
     print(f"filter2d {k}x{k} reflect: tiled {a:.3f} ms ({gbs:.0f} GB/s, {gbs/6568*100:.1f}%)  generic {b:.3f} ms  x{b/a:.2f}", flush=True)
 for k in (3, 5, 11, 17):
@@ -33,7 +33,7 @@ mx = (960 + (xs - 960) * (1 + 0.02 * r2))[None].contiguous()
 my = (540 + (ys - 540) * (1 + 0.02 * r2))[None].contiguous()
 f = lambda: K.remap(x, mx, my, align_corners=True)
 a = t(f)
-os.environ["KB200_DISABLE_TMA"] = "1"; b = t(f, 3); del os.environ["KB200_DISABLE_TMA"]
+K.config.set("tma", 0); b = t(f, 3); K.config.reset()
 gbs = 24.0 * B * 1080 * 1920 / a / 1e6   # shared map: 8 B/pixel of map traffic is read once and stays in L2
 print(f"remap (shared radial map): tiled {a:.3f} ms ({gbs:.0f} GB/s of image traffic, {gbs/6568*100:.1f}%)  generic {b:.3f} ms  x{b/a:.2f}", flush=True)
 mxb, myb = mx.expand(B, -1, -1).contiguous(), my.expand(B, -1, -1).contiguous()

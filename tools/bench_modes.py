@@ -23,9 +23,9 @@ for mode in ("bilinear", "nearest", "bicubic"):
     for pad in ("zeros", "border", "reflection", "fill"):
         f = lambda: K.warp_perspective(src, M, (1080, 1920), mode=mode, padding_mode=pad, fill_value=fv)
         a = t(f); va = _lib.last_warp_variant()
-        os.environ["KB200_DISABLE_TMA"] = "1"
+        K.config.set("tma", 0)
         b = t(f, 3); vb = _lib.last_warp_variant()
-        del os.environ["KB200_DISABLE_TMA"]
+        K.config.reset()
         gbs = 24.0 * B * 1080 * 1920 / a / 1e6
         rows.append(dict(mode=mode, pad=pad, tiled_ms=a, generic_ms=b, speedup=b / a, tiled_GBps=gbs, frac_of_6568=gbs / 6568, variants=[va, vb]))
         print(f"{mode:9s} {pad:11s} tiled {a:7.3f} ms ({gbs:5.0f} GB/s, {gbs/6568*100:4.1f}%)  generic {b:7.3f} ms  x{b/a:.2f}  [{va}/{vb}]", flush=True)

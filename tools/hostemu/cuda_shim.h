@@ -87,6 +87,7 @@ inline size_t __cvta_generic_to_global(const void* p) { return (size_t)p; }
 float __fadd_rd(float, float);
 unsigned __ballot_sync(unsigned, int);
 int __all_sync(unsigned, int);
+int __any_sync(unsigned, int);
 void __syncwarp(unsigned = 0xffffffffu);
 unsigned long long emu_warp_exchange(unsigned long long mine, int src_lane);  // deposit, rendezvous, read src_lane's deposit
 int emu_lane();

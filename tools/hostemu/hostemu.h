@@ -243,6 +243,7 @@ unsigned __ballot_sync(unsigned, int pred) {
     if (w.slot[par][l]) bits |= 1u << l;
   return bits;
 }
+int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 int __all_sync(unsigned m, int pred) {
   const unsigned base = (emu::cur->lin >> 5) * 32, n = blockDim.x * blockDim.y * blockDim.z;
   const unsigned lanes = std::min(32u, n - base);

@@ -1,3 +1,6 @@
+// tools/hostemu reference (NOT product code): round 1's gather-per-tile SSIM kernel, verified on hardware then, kept as the
+// bit-exact reference the emulator runs ssim_vwalk_kernel (the shipped kernel, 2.4-2.9x faster on B200) against.
+//
 // kornia_b200 -- SSIM index map in one pass (fp32, odd Gaussian window K <= 11, 'reflect' border).
 //
 // The reference (kornia/metrics/ssim.py:92-139) runs filter2d_separable five times -- on img1, img2,
@@ -17,14 +20,13 @@
 // separable kernels, so the fused map equals the composition of this library's own filter2d_separable
 // with torch's elementwise ops.
 #pragma once
-#include "filter_generic.cuh"
+#include "../../kornia_b200/csrc/filter_generic.cuh"
 
 namespace kb200 {
 
 constexpr int SSIM_TW = 64;
 constexpr int SSIM_TH = 32;
 constexpr int SSIM_BW = SSIM_TW + 16;  // row stride of the input tiles: room for whole float4 windows
-constexpr int SSIM_MAX_K = 11;
 
 struct SsimParams {
   const float* a;     // img1 (planes,H,W)

@@ -14,8 +14,10 @@
 #include "../../kornia_b200/csrc/gradient_tiled.cuh"
 #include "../../kornia_b200/csrc/sepfilter_vwalk.cuh"
 #include "../../kornia_b200/csrc/ssim_vwalk.cuh"
-#include "../../kornia_b200/csrc/remap_warp.cuh"
+#include "../../kornia_b200/csrc/remap_tiled.cuh"
+#include "ref_ssim_tiled.cuh"
 #include "../../kornia_b200/csrc/warp_bwd_tma2.cuh"
+#include "../../kornia_b200/csrc/warp_bwd_tma3.cuh"
 #include "../../kornia_b200/csrc/warp_u8_tiled.cuh"
 
 #include <random>
@@ -30,8 +32,7 @@ alignas(128) unsigned char ssimv_smem[256 * 1024];
 alignas(128) float ssim_smem[64 * 1024];
 alignas(128) unsigned char remap_smem[256 * 1024];
 alignas(128) unsigned char tma_smem[256 * 1024];
-alignas(128) unsigned char remapw_smem[256 * 1024];
-alignas(128) unsigned char bwd_smem[256 * 1024];
+alignas(128) unsigned char bwd3_smem[256 * 1024];
 alignas(128) unsigned char bwd2_smem[256 * 1024];
 alignas(128) unsigned char u8t_smem[256 * 1024];
 void set_error(const char*, ...) {}
@@ -337,22 +338,6 @@ static void test_undistort(int B, int H, int W, bool lazy, bool strong = false) 
     emu::launch3(grid, dim3(256), [&] { remap_tiled_kernel<3, KB200_ZEROS, true, true>(map, p); });
     compare("remap_tiled_kernel<LENS> (fused undistort) vs maps + remap " + tag, o2, o1, n);
   }
-  {  // the warp-pipelined persistent kernels, on grids that cut the schedule into segments
-    emu::set_smem(remapw_smem, sizeof(remapw_smem));
-    const CUtensorMap wmap = emu::make_map(src, W, H, B * C, 72, REMAPW_SH, C);
-    const unsigned g2 = 1 + (unsigned)((H + W) % 5);
-    for (size_t i = 0; i < n; ++i) o2[i] = -55.f;
-    RemapTiledParams p{src, mx, my, o2, B, H, W, H, W, B, 0, nullptr};
-    const long long lds0 = tma::emu_lds_count();
-    emu::launch(g2, dim3(256), [&] { remap_warp_kernel<3, KB200_ZEROS, true, false>(wmap, p); });
-    printf("     remap_warp_kernel: %.0f %% of the pixels served from the per-warp windows\n", 100.0 * (double)(tma::emu_lds_count() - lds0) / 12.0 / (double)npix);
-    compare("remap_warp_kernel (per-warp pipelines) vs remap_tiled_kernel   " + tag + " grid=" + std::to_string(g2), o2, o1, n);
-    for (size_t i = 0; i < n; ++i) o2[i] = -55.f;
-    RemapTiledParams pl{src, nullptr, nullptr, o2, B, H, W, H, W, B, 0, lens.data()};
-    emu::launch(g2, dim3(256), [&] { remap_warp_kernel<3, KB200_ZEROS, true, true>(wmap, pl); });
-    compare("remap_warp_kernel<LENS> (fused undistort) vs remap_tiled_kernel " + tag + " grid=" + std::to_string(g2), o2, o1, n);
-    emu::set_smem(remap_smem, sizeof(remap_smem));
-  }
 }
 
 
@@ -381,7 +366,7 @@ static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool 
   TmaWarpParams p{};
   const float fillc[3] = {0.25f, 0.5f, 0.75f};
   p.src = src; p.m = m.data(); p.bx = bx.data(); p.by = by.data(); p.fill = fillc;
-  p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.align = 1; p.debug_copy_only = 0; p.only_class = 0;
+  p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.align = 1; p.only_class = 0;
   // oracle: the exact per-pixel path of the same header (the generic kernel's arithmetic, verified against torch on hardware)
   p.out = o2;
   for (int b = 0; b < B; ++b)
@@ -461,7 +446,7 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
   }
   const int nstrips = B * ceil_div(h, 32), max_segs = nstrips / (int)grid + 2;
   const size_t rows = (size_t)grid * max_segs;
-  long long exact[3] = {0, 0, 0};
+  long long exact[4] = {0, 0, 0, 0};
   auto run = [&](int version, float* gsrc, std::vector<double>& gm) {
     emu_exact_path_pixels = 0;
     for (size_t i = 0; i < ns; ++i) gsrc[i] = 0.f;
@@ -470,16 +455,15 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
     TmaBwdParams p{};
     p.gout = gout; p.src = src; p.m = m.data(); p.bx = bx.data(); p.by = by.data(); p.gsrc = gsrc;
     p.records = records.data(); p.record_batch = rb.data();
-    p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.max_segs = max_segs; p.debug = 0;
+    p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.max_segs = max_segs;
     const CUtensorMap mgsrc = emu::make_map(gsrc, W, H, B * C, 72, BWD_SH, C), mgout = emu::make_map(gout, w, h, B * C, 64, 32, C);
-    if (version == 1) {
-      emu::set_smem(bwd_smem, sizeof(bwd_smem));
-      const CUtensorMap msrc = emu::make_map(src, W, H, B * C, 72, 40, C);
-      emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma<C, KB200_ZEROS, PROJ, ALIGN, true, true>(msrc, mgsrc, mgout, p); });
-    } else {
-      emu::set_smem(bwd2_smem, sizeof(bwd2_smem));
-      const CUtensorMap mwin = emu::make_map(src, W, H, B * C, 72, BWD_SH, C);
+    if (version == 2) emu::set_smem(bwd2_smem, sizeof(bwd2_smem));
+    else emu::set_smem(bwd3_smem, sizeof(bwd3_smem));
+    const CUtensorMap mwin = emu::make_map(src, W, H, B * C, 72, BWD_SH, C);
+    if (version == 2) {
       emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true>(mwin, mgsrc, mgout, p); });
+    } else {
+      emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma3<C, KB200_ZEROS, PROJ, ALIGN, true, true>(mwin, mgsrc, mgout, p); });
     }
     exact[version] = emu_exact_path_pixels;
     gm.assign((size_t)B * 9, 0.0);
@@ -493,8 +477,8 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
   float* g1 = aligned(g1s, ns);
   float* g2 = aligned(g2s, ns);
   std::vector<double> gm1, gm2;
-  run(1, g1, gm1);
-  run(2, g2, gm2);
+  run(2, g1, gm1);
+  run(3, g2, gm2);
   auto check = [&](const char* name, const float* g, const std::vector<double>& gm) {
     double num = 0, den = 0, worst = 0;
     for (size_t i = 0; i < ns; ++i) {
@@ -509,9 +493,9 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
     printf("%s %-58s %s  d/dsrc rel-L2 %.2e max-abs %.2e, d/dM rel-L2 %.2e\n", ok ? "ok  " : "FAIL", name, tag.c_str(), e_src, worst, e_m);
     if (!ok) ++failures;
   };
-  printf("     pixels on the exact (global-memory) path: warp_bwd_tma %lld, warp_bwd_tma2 %lld of %d\n", exact[1], exact[2], B * h * w);
-  check("warp_bwd_tma (verified on hw) vs fp64 scalar backward", g1, gm1);
-  check("warp_bwd_tma2 (per-warp pipelines) vs fp64 scalar backward", g2, gm2);
+  printf("     pixels on the exact (global-memory) path: warp_bwd_tma2 %lld, warp_bwd_tma3 %lld of %d\n", exact[2], exact[3], B * h * w);
+  check("warp_bwd_tma2 (per-warp pipelines, verified on hw) vs fp64 scalar backward", g1, gm1);
+  check("warp_bwd_tma3 (4-pixel units) vs fp64 scalar backward", g2, gm2);
 }
 
 // Random shapes, grids and completion modes (run_emu --fuzz N): shakes out the edge cases the fixed list does not name

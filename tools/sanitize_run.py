@@ -43,16 +43,16 @@ KT.build_laplacian_pyramid(src, 3)
 KT.resize(src, (40, 77), antialias=True)
 cam = torch.tensor([[150.0, 0.0, 96.0], [0.0, 150.0, 50.0], [0.0, 0.0, 1.0]], device=dev).expand(B, 3, 3).contiguous()
 KC.undistort_image(src, cam, torch.tensor([[-0.2, 0.05, 0.001, -0.002, 0.01]], device=dev).expand(B, 5).contiguous())
-# uint8 ingest warps: the tiled kernel (W % 4 == 0), the per-tap kernel (odd width; KB200_U8_SIMPLE=1), partial tiles, every padding
+# uint8 ingest warps: the tiled kernel (W % 4 == 0), the per-tap kernel (odd width; switch u8_tiled = 0), partial tiles, every padding
 for shape in ((3, 100, 192, 3), (2, 33, 45, 3), (2, 70, 132, 1), (1, 5, 4, 3), (2, 40, 64, 4)):
     frames = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).to(dev)
     Mq = M[: shape[0]].clone()
-    for simple in ("0", "1"):
-        os.environ["KB200_U8_SIMPLE"] = simple
+    for tiled in (1, 0):
+        K.config.set("u8_tiled", tiled)
         for pad in ("zeros", "border", "reflection"):
             KT.warp_perspective_from_uint8(frames, Mq, (shape[1] + 3, shape[2] - 1), padding_mode=pad)
             KT.warp_affine_from_uint8(frames, Mq[:, :2].contiguous(), (shape[1], shape[2]), padding_mode=pad, align_corners=False)
-    os.environ.pop("KB200_U8_SIMPLE")
+    K.config.reset()
     if shape[3] == 3:
         KT.warp_perspective_from_uint8(frames, Mq, (shape[1], shape[2]), mode="bicubic", padding_mode="fill", fill_value=torch.tensor([0.1, 0.2, 0.3]))
         KT.warp_perspective_from_uint8(frames, Mq, (shape[1], shape[2]), padding_mode="fill", fill_value=torch.tensor([0.1, 0.2, 0.3]))
@@ -61,4 +61,4 @@ for shape in ((3, 100, 192, 3), (2, 70, 132, 1), (1, 33, 45, 3)):  # the last on
     camq = torch.tensor([[0.8 * shape[2], 0.0, shape[2] / 2], [0.0, 0.8 * shape[2], shape[1] / 2], [0.0, 0.0, 1.0]], device=dev).expand(shape[0], 3, 3).contiguous()
     KC.undistort_image_from_uint8(frames, camq, torch.tensor([[-0.2, 0.05, 0.001, -0.002, 0.01]], device=dev).expand(shape[0], 5).contiguous())
 torch.cuda.synchronize()
-print("sanitize workload done" + (" (KB200_OPTIN=all)" if os.environ.get("KB200_OPTIN") == "all" else ""))
+print("sanitize workload done")
