@@ -663,6 +663,33 @@ def run_small(args) -> None:
             for name, fn in cases(R).items():  # the reference composition in torch eager on THIS GPU
                 ips, us = throughput(fn, 0.5)
                 rows[name].update({"torch_eager_here_img_s": ips, "vs_torch_eager_here": rows[name]["ours_img_s"] / ips})
+    # class API (benchmarks/README.md:195-199 publishes CPU / MPS numbers only): parameter sampling on the device
+    # + application, p = 1.  "torch_composition_here" = the same classes with the image functions swapped for the oracle's
+    # torch composition on this GPU (the reference's classes cannot travel to the GPU box).
+    import importlib
+
+    A = importlib.import_module("kornia_b200.augmentation")
+    published_cpu = {"RandomPerspective": 843, "RandomAffine": 899, "RandomGaussianBlur": 1103}
+    swaps = {"warp_perspective": R.warp_perspective, "warp_affine": R.warp_affine, "gaussian_blur2d": R.gaussian_blur2d,
+             "get_perspective_transform": R.get_perspective_transform, "get_rotation_matrix2d": R.get_rotation_matrix2d}
+    aug_rows = {}
+    with torch.no_grad():
+        for name, make in (("RandomPerspective", lambda: A.RandomPerspective(0.5, p=1.0)),
+                           ("RandomAffine", lambda: A.RandomAffine(30.0, translate=(0.1, 0.1), scale=(0.8, 1.2), shear=10.0, p=1.0)),
+                           ("RandomGaussianBlur", lambda: A.RandomGaussianBlur((5, 5), (0.1, 2.0), p=1.0))):
+            aug = make().to(dev)
+            ips, us = throughput(lambda: aug(x))
+            aug_rows[name] = {"ours_img_s": ips, "ours_us_per_call": us, "published_cpu_eager_apple": published_cpu[name]}
+            if not args.no_side_legs:
+                saved = {k: getattr(A, k) for k in swaps}
+                try:
+                    for k, v in swaps.items():
+                        setattr(A, k, v)
+                    ips_t, _ = throughput(lambda: aug(x), 0.5)
+                finally:
+                    for k, v in saved.items():
+                        setattr(A, k, v)
+                aug_rows[name].update({"torch_composition_here_img_s": ips_t, "vs_torch_composition_here": ips / ips_t})
     head = rows["warp_perspective"]
     line = {"metric": "img/s warp_perspective 32x3x256x256 fwd bilinear fp32 (back-to-back calls, wall clock, host cost included)", "value": head["ours_img_s"],
             "unit": "img/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
@@ -670,7 +697,7 @@ def run_small(args) -> None:
             "config": {"workload": "benchmarks/geometry/flagship.py operating point: batch 32, 256x256, fp32; rotate 30 deg about the centre, corner quad jittered by 8*randn px",
                        "baseline": "benchmarks/README.md:154-157, RTX PRO 6000 Blackwell, kornia + torch.compile (other hardware: published context, not a same-box comparison)",
                        "timing": ">= 1 s of back-to-back calls per op, one synchronize per 100 calls, wall clock"},
-            "ops": rows, "gpu_launches": launches}
+            "ops": rows, "augmentation_classes": aug_rows, "gpu_launches": launches}
     print(json.dumps(line), flush=True)
 
 

@@ -84,7 +84,6 @@ enum Option {
   OPT_SEP_VWALK,       // band-walking separable filter: -1 auto (13 taps and more), 0 never, 1 whenever it applies
   OPT_TILED_GRADIENT,  // shared-memory derivative stencils (off: gradient.cuh)
   OPT_U8_TILED,        // staged-window uint8 ingest warp (off: per-tap kernel)
-  OPT_BWD_V3,          // 4-pixel-unit tiled backward (off: warp_bwd_tma2)
   OPT_COUNT
 };
 int option(Option o);

@@ -52,8 +52,7 @@ int warp_tma_backward(const float* gout, const float* src, const float* m, const
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return KB200_EUNSUPPORTED;
   }
-  const int rc = option(OPT_BWD_V3) ? launch_warp_bwd_tma3(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, st)
-                                    : launch_warp_bwd_tma2(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, st);
+  const int rc = launch_warp_bwd_tma2(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, st);
   if (rc != KB200_OK || !gm) return rc;
   warp_gm_reduce_records<<<dim3(9, Bm), 256, 0, st>>>(p.records, p.record_batch, gm, (int)rows, Bm);
   cudaError_t e = cudaGetLastError();

@@ -1,6 +1,6 @@
 // kornia_b200 -- shared pieces of the tiled fused warp backward kernels (fp32, bilinear, zeros/border, C = 3 or 1):
 // parameters, the exact per-pixel path, the fixed-order second stage of d/dM and the host-side sizing.  The kernels are
-// warp_bwd_tma2.cuh (every warp its own pipeline) and warp_bwd_tma3.cuh (4-pixel straight-line units).
+// warp_bwd_tma2.cuh (every warp its own pipeline).
 //
 // Replaces grid_sampler_2d_backward (atomic scatter into a zero-filled tensor + a dense grad_grid) and the autograd of the
 // ~15 broadcast elementwise ops of kornia/geometry/transform/imgwarp.py:165-170.
@@ -12,7 +12,9 @@
 //     strip segment, then warp-shuffle -> one record per (CTA, segment, warp); a second kernel sums the records in a fixed
 //     order (deterministic, double accumulation).
 // History: round 1's first structure (one shared stage per CTA, CTA-wide mbarrier hand-off per tile) measured 1.90 ms at
-// B=128x3x720x1280 against 1.68 ms for warp_bwd_tma2 on the same B200 (profiles/r2_bench_warp_bwd_*.json) and was removed.
+// B=128x3x720x1280 against 1.68 ms for warp_bwd_tma2 on the same B200 and was removed; so was a third structure (4-pixel
+// straight-line units on stride-1 lanes with rank-ordered rounds for lanes sharing a cell): its lane predicates compiled to
+// BSSY / BSYNC regions, 286 thread-instructions per pixel against 254, 2.15 ms (profiles/r2_bwd_tma3_ncu_digest.txt).
 #pragma once
 #include "warp_tma.cuh"
 
@@ -116,8 +118,6 @@ inline size_t bwd_tma_workspace_bytes(int B, int h) {
 }
 
 // msrcwin: tensor map of `src` with the per-warp window box (72, BWD_SH, C).
-int launch_warp_bwd_tma3(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const CUtensorMap& mgout, const TmaBwdParams& p, int C, int pad,
-                         int projective, int align, bool need_src, bool need_m, cudaStream_t st);
 int launch_warp_bwd_tma2(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const CUtensorMap& mgout, const TmaBwdParams& p, int C, int pad,
                          int projective, int align, bool need_src, bool need_m, cudaStream_t st);
 

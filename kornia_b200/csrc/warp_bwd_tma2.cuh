@@ -22,6 +22,8 @@
 // Measured on B200 (round 2): bit-identical d/dsrc up to the order of the TMA reduce-adds; 1.68 ms at B=128x3x720x1280 with
 // both gradients (round 1's shared-stage kernel: 1.90 ms).
 #pragma once
+#include <type_traits>
+
 #include "warp_bwd_tma.cuh"
 
 namespace kb200 {
@@ -148,7 +150,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
       // cell (ly, lx) of the window / strip = (Y - MAGIC - soy, X - MAGIC - sox)
       const unsigned kwin = (unsigned)(FLOOR_MAGIC_BITS + soy) * (unsigned)BW + (unsigned)(FLOOR_MAGIC_BITS + sox);
       const uint32_t strip_base = strip_u32 - 4u * kwin, win_base = win_u32 - 4u * kwin;
-      const float s_lo_x = (float)sox, s_hi_x = (float)(sox + BW - 1), s_lo_y = (float)soy, s_hi_y = (float)(soy + BWD_SH - 1);
+      // A window that starts at the image edge also serves coordinates in [-1, 0) under 'zeros': the tap in column / row -1
+      // is outside the image (no contribution, value 0) and is predicated off in the EDGE copy of the row loop below.  Before,
+      // every pixel of such a tile -- one tile in ten at 720p -- took the per-pixel atomics path.
+      const bool edge_x = PAD == KB200_ZEROS && sox == 0, edge_y = PAD == KB200_ZEROS && soy == 0;
+      const float s_lo_x = edge_x ? -1.f : (float)sox, s_hi_x = (float)(sox + BW - 1);
+      const float s_lo_y = edge_y ? -1.f : (float)soy, s_hi_y = (float)(soy + BWD_SH - 1);
 
       // upstream gradient, software-pipelined one row ahead: both columns of a lane in one 8-byte load per channel
       float2 go_next[NC];
@@ -163,6 +170,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
       }
       __syncwarp();  // strip cleared by all lanes
 
+      auto rows = [&](auto edge_tag) {
+      constexpr bool EDGE = decltype(edge_tag)::value;
 #pragma unroll 1
       for (int i = 0; i < RPW; ++i) {
         const int y = y_base + i;
@@ -220,17 +229,25 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
 #pragma unroll
             for (int c = 0; c < NC; ++c) go[c] = j == 0 ? go2[c].x : go2[c].y;
             const uint32_t cell = ((unsigned)Y * (unsigned)BW + (unsigned)X) * 4u;
+            // EDGE tiles only: taps in column / row -1 are outside the image
+            const bool west_in = !EDGE || !(edge_x && ix < 0.f), north_in = !EDGE || !(edge_y && iy < 0.f);
             if (NEED_SRC) {
               const uint32_t a = cell + strip_base;
               // tap by tap: lanes hit distinct cells inside one instruction; __syncwarp orders the taps
+              if (west_in && north_in) {
 #pragma unroll
-              for (int c = 0; c < NC; ++c) tma::sts(a + c * SPLANE * 4, tma::lds(a + c * SPLANE * 4) + w_nw * go[c]);
+                for (int c = 0; c < NC; ++c) tma::sts(a + c * SPLANE * 4, tma::lds(a + c * SPLANE * 4) + w_nw * go[c]);
+              }
               __syncwarp();
+              if (north_in) {
 #pragma unroll
-              for (int c = 0; c < NC; ++c) tma::sts(a + (c * SPLANE + 1) * 4, tma::lds(a + (c * SPLANE + 1) * 4) + w_ne * go[c]);
+                for (int c = 0; c < NC; ++c) tma::sts(a + (c * SPLANE + 1) * 4, tma::lds(a + (c * SPLANE + 1) * 4) + w_ne * go[c]);
+              }
               __syncwarp();
+              if (west_in) {
 #pragma unroll
-              for (int c = 0; c < NC; ++c) tma::sts(a + (c * SPLANE + BW) * 4, tma::lds(a + (c * SPLANE + BW) * 4) + w_sw * go[c]);
+                for (int c = 0; c < NC; ++c) tma::sts(a + (c * SPLANE + BW) * 4, tma::lds(a + (c * SPLANE + BW) * 4) + w_sw * go[c]);
+              }
               __syncwarp();
 #pragma unroll
               for (int c = 0; c < NC; ++c)
@@ -243,9 +260,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
               float s_nw = 0.f, s_ne = 0.f, s_sw = 0.f, s_se = 0.f;
 #pragma unroll
               for (int c = 0; c < NC; ++c) {
-                s_nw = fmaf(go[c], tma::lds(t + (c * SPLANE) * 4), s_nw);
-                s_ne = fmaf(go[c], tma::lds(t + (c * SPLANE + 1) * 4), s_ne);
-                s_sw = fmaf(go[c], tma::lds(t + (c * SPLANE + BW) * 4), s_sw);
+                s_nw = fmaf(go[c], (west_in && north_in) ? tma::lds(t + (c * SPLANE) * 4) : 0.f, s_nw);
+                s_ne = fmaf(go[c], north_in ? tma::lds(t + (c * SPLANE + 1) * 4) : 0.f, s_ne);
+                s_sw = fmaf(go[c], west_in ? tma::lds(t + (c * SPLANE + BW) * 4) : 0.f, s_sw);
                 s_se = fmaf(go[c], tma::lds(t + (c * SPLANE + BW + 1) * 4), s_se);
               }
               gix = (s_ne - s_nw) * wy1 + (s_se - s_sw) * wy0;
@@ -269,6 +286,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
           }
         }
       }
+      };
+      if (edge_x || edge_y) rows(std::true_type{});  // warp-uniform
+      else rows(std::false_type{});
       // flush the strip: one TMA reduce-add per warp and tile
       if (NEED_SRC) {
         tma::fence_proxy_async();

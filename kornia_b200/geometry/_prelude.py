@@ -114,4 +114,4 @@ def sampling_matrix(M: torch.Tensor, src_hw, dst_hw, affine: bool) -> torch.Tens
     if not fused_ok:
         M3 = affine_to_homography(M) if affine else M
         return inverse3x3(normalize_homography(M3, src_hw, dst_hw))
-    return _ops.ops.warp_prelude(M, int(src_hw[0]), int(src_hw[1]), int(dst_hw[0]), int(dst_hw[1]), bool(affine))
+    return _ops.prelude(M, src_hw[0], src_hw[1], dst_hw[0], dst_hw[1], affine)

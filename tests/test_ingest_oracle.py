@@ -62,6 +62,7 @@ def device_call_on_cpu(monkeypatch):
     from kornia_b200.geometry.calibration import undistort
 
     monkeypatch.setattr(_ops, "undistort_u8hwc", undistort_mirror)
+    monkeypatch.setattr(_ops, "undistort_fused", lambda *a, **k: (_ for _ in ()).throw(_ops._lib.Unsupported("no device here")))  # fp32 fused kernel
     monkeypatch.setattr(undistort, "remap", R.remap)                              # the composition path (tilt, odd widths)
 
     def take_the_kernel_path():  # undistort only: its host code asks image.is_cuda before calling the C entry

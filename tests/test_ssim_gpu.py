@@ -34,8 +34,10 @@ def test_ssim_forward_matches_reference(name):
         assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want))
     else:
         torch.testing.assert_close(got.cpu(), want, **TOL)
-    fused = kw["window_size"] <= 11
-    assert (K._ops.launch_count - before == 1) == fused, "window <= 11 must take the one-kernel path, larger ones the composition"
+    # one kernel for odd windows up to 11 taps on rows of a multiple of 4 floats (TMA rows are 16-byte aligned); the
+    # composition (five one-pass blurs + torch elementwise ops) otherwise
+    fused = kw["window_size"] <= 11 and ins["img1"].shape[-1] % 4 == 0
+    assert (K._ops.launch_count - before == 1) == fused, (K._ops.launch_count - before, fused)
 
 
 @pytest.mark.parametrize("name", GRAD)
@@ -51,7 +53,7 @@ def test_ssim_grads_match_reference(name):
 def test_fused_ssim_equals_composed_path(ws):
     """One kernel vs this library's differentiable composition (five one-pass separable blurs + torch
     elementwise ops): same taps, same tap order, one rounding per op -> the same map."""
-    a = torch.rand(3, 3, 101, 134, device=DEV)
+    a = torch.rand(3, 3, 101, 136, device=DEV)
     b = (a + 0.2 * torch.randn_like(a)).clamp(0, 1)
     fused = K.metrics.ssim(a, b, ws)
     composed = K.metrics.ssim(a.clone().requires_grad_(True), b, ws).detach()

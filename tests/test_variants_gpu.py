@@ -160,13 +160,12 @@ def test_band_walk_ssim_many_segments_and_golden():
 
 
 # ------------------------------------------------------------------------------------------ tiled backward kernels
-@pytest.mark.parametrize("v3", [0, 1])
 @pytest.mark.parametrize("pad", ["zeros", "border"])
 @pytest.mark.parametrize("ac", [True, False])
 @pytest.mark.parametrize("C", [3, 1])
-def test_tiled_backward_matches_generic(v3, pad, ac, C):
-    """warp_bwd_tma2 / warp_bwd_tma3 (switch bwd_v3) against the generic atomics kernel: same per-pixel arithmetic; d/dsrc
-    differs only by the order of the adds, d/dM by the grouping of the partial sums."""
+def test_tiled_backward_matches_generic(pad, ac, C):
+    """warp_bwd_tma2 against the generic atomics kernel: same per-pixel arithmetic; d/dsrc differs only by the order of the
+    adds, d/dM by the grouping of the partial sums."""
     from test_parity_gpu import _bench_homographies, _generic, _wild_matrices
     from helpers import rel_l2
 
@@ -190,7 +189,6 @@ def test_tiled_backward_matches_generic(v3, pad, ac, C):
 
         for kind in ("persp", "affine"):
             gs0, gm0 = _generic(lambda: grads(kind), check_variant=False)
-            K.config.set("bwd_v3", v3)
             gs2, gm2 = grads(kind)
             (gs_only,) = grads(kind, (True, False))
             (gm_only,) = grads(kind, (False, True))
@@ -205,14 +203,12 @@ def test_tiled_backward_matches_generic(v3, pad, ac, C):
                 assert rel_l2(gm_only[b], gm2[b]) < 1e-5
 
 
-@pytest.mark.parametrize("v3", [0, 1])
-def test_tiled_backward_720p_and_goldens(v3):
+def test_tiled_backward_720p_and_goldens():
     """cfg4's shape at reduced batch against the reference's autograd on CPU, and every golden gradient case."""
     from helpers import rel_l2, run_case
     from oracle import kornia_restated as R
     from test_parity_gpu import _bench_homographies
 
-    K.config.set("bwd_v3", v3)
     H, W, B = 720, 1280, 2
     M = _bench_homographies(B, H, W, 7).to(DEV)
     yy, xx = torch.linspace(0, 1, H)[:, None], torch.linspace(0, 1, W)[None, :]

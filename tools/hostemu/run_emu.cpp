@@ -17,7 +17,6 @@
 #include "../../kornia_b200/csrc/remap_tiled.cuh"
 #include "ref_ssim_tiled.cuh"
 #include "../../kornia_b200/csrc/warp_bwd_tma2.cuh"
-#include "../../kornia_b200/csrc/warp_bwd_tma3.cuh"
 #include "../../kornia_b200/csrc/warp_u8_tiled.cuh"
 
 #include <random>
@@ -32,7 +31,6 @@ alignas(128) unsigned char ssimv_smem[256 * 1024];
 alignas(128) float ssim_smem[64 * 1024];
 alignas(128) unsigned char remap_smem[256 * 1024];
 alignas(128) unsigned char tma_smem[256 * 1024];
-alignas(128) unsigned char bwd3_smem[256 * 1024];
 alignas(128) unsigned char bwd2_smem[256 * 1024];
 alignas(128) unsigned char u8t_smem[256 * 1024];
 void set_error(const char*, ...) {}
@@ -457,14 +455,9 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
     p.records = records.data(); p.record_batch = rb.data();
     p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.max_segs = max_segs;
     const CUtensorMap mgsrc = emu::make_map(gsrc, W, H, B * C, 72, BWD_SH, C), mgout = emu::make_map(gout, w, h, B * C, 64, 32, C);
-    if (version == 2) emu::set_smem(bwd2_smem, sizeof(bwd2_smem));
-    else emu::set_smem(bwd3_smem, sizeof(bwd3_smem));
+    emu::set_smem(bwd2_smem, sizeof(bwd2_smem));
     const CUtensorMap mwin = emu::make_map(src, W, H, B * C, 72, BWD_SH, C);
-    if (version == 2) {
-      emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true>(mwin, mgsrc, mgout, p); });
-    } else {
-      emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma3<C, KB200_ZEROS, PROJ, ALIGN, true, true>(mwin, mgsrc, mgout, p); });
-    }
+    emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true>(mwin, mgsrc, mgout, p); });
     exact[version] = emu_exact_path_pixels;
     gm.assign((size_t)B * 9, 0.0);
     for (size_t r = 0; r < rows; ++r)
@@ -478,7 +471,6 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
   float* g2 = aligned(g2s, ns);
   std::vector<double> gm1, gm2;
   run(2, g1, gm1);
-  run(3, g2, gm2);
   auto check = [&](const char* name, const float* g, const std::vector<double>& gm) {
     double num = 0, den = 0, worst = 0;
     for (size_t i = 0; i < ns; ++i) {
@@ -493,9 +485,8 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
     printf("%s %-58s %s  d/dsrc rel-L2 %.2e max-abs %.2e, d/dM rel-L2 %.2e\n", ok ? "ok  " : "FAIL", name, tag.c_str(), e_src, worst, e_m);
     if (!ok) ++failures;
   };
-  printf("     pixels on the exact (global-memory) path: warp_bwd_tma2 %lld, warp_bwd_tma3 %lld of %d\n", exact[2], exact[3], B * h * w);
-  check("warp_bwd_tma2 (per-warp pipelines, verified on hw) vs fp64 scalar backward", g1, gm1);
-  check("warp_bwd_tma3 (4-pixel units) vs fp64 scalar backward", g2, gm2);
+  printf("     pixels on the exact (global-memory) path: warp_bwd_tma2 %lld of %d\n", exact[2], B * h * w);
+  check("warp_bwd_tma2 (per-warp pipelines) vs fp64 scalar backward", g1, gm1);
 }
 
 // Random shapes, grids and completion modes (run_emu --fuzz N): shakes out the edge cases the fixed list does not name
