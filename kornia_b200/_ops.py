@@ -390,6 +390,30 @@ def remap(image, map_x, map_y, normalized, interp, pad, align):
 # ---------------------------------------------------------------------------------------------
 # filter2d: depthwise correlation with the border folded into the index; kernel (Bk,kh,kw) already flipped / normalised
 # ---------------------------------------------------------------------------------------------
+MAX_PLANES = 65535  # gridDim.z / plane-count limit of one filter launch (the warp kernels chunk inside the C library)
+
+
+def _plane_chunks(B: int, C: int):
+    """Batch ranges [b0, b1) whose plane count B'*C fits one launch: feature maps like B=256, C=256 are served by several
+    launches over batch slices (samples are independent; a sample's C planes stay together so kernels keep cycling over
+    samples as in filter.py:131,141-142)."""
+    if B * C <= MAX_PLANES:
+        return [(0, B)]
+    if C > MAX_PLANES:
+        raise RuntimeError(f"kornia_b200: {C} channels per sample exceed the {MAX_PLANES}-plane launch limit")
+    step = MAX_PLANES // C
+    return [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
+
+
+def _kernel_rows(kernel: torch.Tensor, b0: int, b1: int) -> torch.Tensor:
+    """Kernels of the samples [b0, b1): sample b uses kernel row b mod Bk."""
+    Bk = kernel.shape[0]
+    if Bk == 1:
+        return kernel
+    idx = torch.arange(b0, b1, device=kernel.device) % Bk
+    return kernel.index_select(0, idx).contiguous()
+
+
 def _filter_out_hw(H, W, kh, kw, same):
     return (H, W) if same else (max(H - kh + 1, 0), max(W - kw + 1, 0))
 
@@ -408,9 +432,11 @@ def _filter2d_call(xc, kc, border, same):
     out = torch.empty((B, C) + _filter_out_hw(H, W, kh, kw, same), device=xc.device, dtype=xc.dtype)
     if out.numel() > 0:
         with torch.cuda.device(xc.device), _Timed("filter2d_forward", xc):
-            _lib.call("kb200_filter2d_forward", _ptr(xc), _ptr(kc), _ptr(out), B, C, H, W, Bk, kh, kw, border, int(same), _dtype_code(xc),
-                      _stream(xc))
-        _bump()
+            for b0, b1 in _plane_chunks(B, C):
+                k = kc if (b0, b1) == (0, B) else _kernel_rows(kc, b0, b1)
+                _lib.call("kb200_filter2d_forward", _ptr(xc[b0:b1]), _ptr(k), _ptr(out[b0:b1]), b1 - b0, C, H, W, k.shape[0], kh, kw, border,
+                          int(same), _dtype_code(xc), _stream(xc))
+                _bump()
     return out
 
 
@@ -437,9 +463,11 @@ def _filter2d_bwd_input_cuda(gout, kernel, H, W, border, same):
         return gx.zero_()
     if gx.numel() > 0:
         with torch.cuda.device(gout.device), _Timed("filter2d_backward_input", gout):
-            _lib.call("kb200_filter2d_backward_input", _ptr(gout), _ptr(k), _ptr(gx), B, C, H, W, Bk, kh, kw, border, int(same), _dtype_code(gout),
-                      _stream(gout))
-        _bump()
+            for b0, b1 in _plane_chunks(B, C):
+                kk = k if (b0, b1) == (0, B) else _kernel_rows(k, b0, b1)
+                _lib.call("kb200_filter2d_backward_input", _ptr(gout[b0:b1]), _ptr(kk), _ptr(gx[b0:b1]), b1 - b0, C, H, W, kk.shape[0], kh, kw,
+                          border, int(same), _dtype_code(gout), _stream(gout))
+                _bump()
     return gx
 
 
@@ -450,12 +478,25 @@ def _filter2d_bwd_kernel_cuda(gout, x, Bk, kh, kw, border, same):
     gk = torch.empty((Bk, kh, kw), device=x.device, dtype=x.dtype)
     if gout.numel() == 0 or x.numel() == 0:
         return gk.zero_()
+    chunks = _plane_chunks(B, C)
     with torch.cuda.device(x.device), _Timed("filter2d_backward_kernel", x):
-        nbytes = _lib.load().kb200_filter2d_backward_kernel_workspace_bytes(B, C, H, W, Bk, kh, kw, dt)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        _lib.call("kb200_filter2d_backward_kernel", _ptr(gout), _ptr(x), _ptr(gk), _ptr(ws), B, C, H, W, Bk, kh, kw, border, int(same), dt,
-                  _stream(x))
-    _bump(2)
+        if len(chunks) == 1:
+            nbytes = _lib.load().kb200_filter2d_backward_kernel_workspace_bytes(B, C, H, W, Bk, kh, kw, dt)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _lib.call("kb200_filter2d_backward_kernel", _ptr(gout), _ptr(x), _ptr(gk), _ptr(ws), B, C, H, W, Bk, kh, kw, border, int(same), dt,
+                      _stream(x))
+            _bump(2)
+        else:  # per-sample kernel gradients of each slice, folded onto the Bk kernel rows (sample b feeds row b mod Bk)
+            gk.zero_()
+            for b0, b1 in chunks:
+                n = b1 - b0
+                part = torch.empty((n, kh, kw), device=x.device, dtype=x.dtype)
+                nbytes = _lib.load().kb200_filter2d_backward_kernel_workspace_bytes(n, C, H, W, n, kh, kw, dt)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                _lib.call("kb200_filter2d_backward_kernel", _ptr(gout[b0:b1]), _ptr(x[b0:b1]), _ptr(part), _ptr(ws), n, C, H, W, n, kh, kw, border,
+                          int(same), dt, _stream(x))
+                _bump(2)
+                gk.index_add_(0, torch.arange(b0, b1, device=x.device) % Bk, part)
     return gk
 
 
@@ -513,9 +554,12 @@ def _sepfilter_fwd_cuda(x, kx, ky, border, same):
     if out.numel() > 0:
         try:
             with torch.cuda.device(x.device), _Timed("sepfilter_forward", x):
-                _lib.call("kb200_sepfilter_forward", _ptr(xc), _ptr(kxc), _ptr(kyc), _ptr(out), B, C, H, W, Bkx, kw, Bky, kh, border,
-                          int(same), dt, _stream(x))
-            _bump()
+                for b0, b1 in _plane_chunks(B, C):
+                    whole = (b0, b1) == (0, B)
+                    kxs, kys = (kxc, kyc) if whole else (_kernel_rows(kxc, b0, b1), _kernel_rows(kyc, b0, b1))
+                    _lib.call("kb200_sepfilter_forward", _ptr(xc[b0:b1]), _ptr(kxs), _ptr(kys), _ptr(out[b0:b1]), b1 - b0, C, H, W, kxs.shape[0], kw,
+                              kys.shape[0], kh, border, int(same), dt, _stream(x))
+                    _bump()
         except _lib.Unsupported:
             # kernels too large for the one-pass shared-memory tile: two 1-D passes of the 2-D kernel
             mid = _filter2d_call(xc, kxc[:, None, :].contiguous(), border, same)

@@ -114,9 +114,19 @@ class _RandomAugmentation2D(nn.Module):
         self.set_rng_device_and_dtype(device if device is not None else self.device, dtype if dtype is not None else self.dtype)
         return super().to(*args, **kwargs)
 
-    def _uniform(self, lo, hi) -> Uniform:
-        return Uniform(torch.as_tensor(lo, device=self.device, dtype=self.dtype), torch.as_tensor(hi, device=self.device, dtype=self.dtype),
+    def _uniform(self, lo, hi, key: Optional[str] = None) -> Uniform:
+        """Uniform(lo, hi) on the generator device; ``key`` caches the sampler (and its two scalar tensors) across calls --
+        building them is ~10 host-side tensor ops per call otherwise.  set_rng_device_and_dtype / .to() drop the cache."""
+        cache = getattr(self, "_samplers", None)
+        if cache is None:
+            cache = self._samplers = {}
+        if key is not None and key in cache:
+            return cache[key]
+        dist = Uniform(torch.as_tensor(lo, device=self.device, dtype=self.dtype), torch.as_tensor(hi, device=self.device, dtype=self.dtype),
                        validate_args=False)
+        if key is not None:
+            cache[key] = dist
+        return dist
 
     def _gate(self, batch: int) -> torch.Tensor:
         """base.py:165-196: batch gate, then element gate; the draws (torch.rand on the generator device) in that order."""
@@ -219,7 +229,7 @@ class RandomPerspective(_RandomAugmentation2D):
             raise AssertionError(f"'distortion_scale' must be a scalar within [0, 1]. Got {scale}.")
         start = torch.tensor([[[0.0, 0], [width - 1, 0], [width - 1, height - 1], [0, height - 1]]], device=dev, dtype=dt).expand(B, -1, -1)
         factor = torch.stack([scale * width / 2, scale * height / 2], dim=0).view(-1, 1, 2)
-        rand_val = _rsample(start.shape, self._uniform(0, 1), self.same_on_batch)
+        rand_val = _rsample(start.shape, self._uniform(0, 1, "unit"), self.same_on_batch)
         if self.sampling_method == "basic":
             offset = factor * rand_val * torch.tensor([[[1, 1], [-1, 1], [-1, -1], [1, -1]]], device=dev, dtype=dt)
         else:
@@ -270,23 +280,25 @@ class RandomAffine(_RandomAugmentation2D):
         """random_generator/_2d/affine.py:160-222: angle, scale (x, then y), translate x, translate y, shear x, shear y."""
         B, height, width = batch_shape[0], batch_shape[-2], batch_shape[-1]
         dev, dt, same = self.device, self.dtype, self.same_on_batch
-        deg, tr, sc, sh = self._ranges()
-        angle = _rsample((B,), self._uniform(deg[0], deg[1]), same)
+        if getattr(self, "_range_cache", None) is None:
+            self._range_cache = self._ranges()
+        deg, tr, sc, sh = self._range_cache
+        angle = _rsample((B,), self._uniform(deg[0], deg[1], "angle"), same)
         if sc is not None:
-            scale = _rsample((B,), self._uniform(sc[0], sc[1]), same).unsqueeze(1).repeat(1, 2)
+            scale = _rsample((B,), self._uniform(sc[0], sc[1], "scale_x"), same).unsqueeze(1).repeat(1, 2)
             if sc.numel() == 4:
-                scale[:, 1] = _rsample((B,), self._uniform(sc[2], sc[3]), same)
+                scale[:, 1] = _rsample((B,), self._uniform(sc[2], sc[3], "scale_y"), same)
         else:
             scale = torch.ones((B, 2), device=dev, dtype=dt)
         if tr is not None:
-            translations = torch.stack([_rsample((B,), self._uniform(-tr[0], tr[0]), same) * width,
-                                        _rsample((B,), self._uniform(-tr[1], tr[1]), same) * height], dim=-1)
+            translations = torch.stack([_rsample((B,), self._uniform(-tr[0], tr[0], "tx"), same) * width,
+                                        _rsample((B,), self._uniform(-tr[1], tr[1], "ty"), same) * height], dim=-1)
         else:
             translations = torch.zeros((B, 2), device=dev, dtype=dt)
         center = (torch.tensor([width, height], device=dev, dtype=dt).view(1, 2) / 2.0 - 0.5).expand(B, -1)
         if sh is not None:
-            sx = _rsample((B,), self._uniform(sh[0][0], sh[0][1]), same)
-            sy = _rsample((B,), self._uniform(sh[1][0], sh[1][1]), same)
+            sx = _rsample((B,), self._uniform(sh[0][0], sh[0][1], "shear_x"), same)
+            sy = _rsample((B,), self._uniform(sh[1][0], sh[1][1], "shear_y"), same)
         else:
             sx = torch.zeros(B, device=dev, dtype=dt)
             sy = torch.zeros(B, device=dev, dtype=dt)
@@ -317,7 +329,7 @@ class RandomGaussianBlur(_RandomAugmentation2D):
 
     def generate_parameters(self, batch_shape):
         s = self.sigma if isinstance(self.sigma, torch.Tensor) else torch.tensor(self.sigma)
-        return {"sigma": _rsample((batch_shape[0],), self._uniform(s[0], s[1]), self.same_on_batch)}
+        return {"sigma": _rsample((batch_shape[0],), self._uniform(s[0], s[1], "sigma"), self.same_on_batch)}
 
     def apply_transform(self, input, params, flags, transform=None):
         sigma = params["sigma"].to(input).unsqueeze(-1).expand(-1, 2)

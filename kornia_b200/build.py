@@ -12,6 +12,7 @@ OUT_DIR = os.path.join(_HERE, "_C")
 OUT = os.path.join(OUT_DIR, "libkornia_b200.so")
 
 NVCC_FLAGS = [
+    "-Xfatbin", "-compress-all",
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",

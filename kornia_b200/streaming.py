@@ -95,6 +95,7 @@ def _prefer_memory_node(node: int) -> bool:
 
 
 _BOUND: dict = {}
+_BINDING_DISABLED = os.environ.get("KB200_NO_NUMA_BIND", "") == "1"  # read once: measurement aid (the unbound contrast run)
 
 
 def bind_to_device_numa_node(device_index: int, sysfs: str = "/sys") -> dict:
@@ -105,6 +106,10 @@ def bind_to_device_numa_node(device_index: int, sysfs: str = "/sys") -> dict:
     if device_index in _BOUND:
         return _BOUND[device_index]
     info = {"node": None, "cpus": 0, "affinity": False, "mempolicy": False}
+    if _BINDING_DISABLED:
+        info["disabled"] = True
+        _BOUND[device_index] = info
+        return info
     node = device_numa_node(device_index, sysfs)
     if node is not None:
         cpus = node_cpus(node, sysfs)

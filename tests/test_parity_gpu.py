@@ -61,6 +61,22 @@ def test_warp_forward_fp64_matches_oracle(name):
         torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("name", FWD_WARP)
+def test_warp_forward_fp32_equals_the_same_device_reference(name):
+    """fp32, every golden case (3 interpolations x 4 paddings x both align_corners, remap included) against the reference
+    composition on the SAME GPU with cuDNN off: the coordinate chain is replicated op for op, so there is no tie to flip and
+    no tolerance to grant -- nearest included.  (The tolerance of the CPU-golden tests above is the reference's own CPU-vs-CUDA
+    gap, not this library's.)"""
+    op, kw, ins, _ = WARP.case(name)
+    got = run_case(K, op, kw, ins, device=DEV)
+    with torch.backends.cudnn.flags(enabled=False):
+        want = run_case(R, op, kw, ins, device=DEV)
+    if kw["mode"] == "bicubic":  # ATen's bicubic kernel contracts its weight polynomials with FMAs of its own choosing
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-6)
+    else:
+        assert torch.equal(got, want), float((got - want).abs().max())
+
+
 GRAD_WARP = [n for op in ("warp_perspective_grad", "warp_affine_grad", "remap_grad") for n in WARP.names(op)]
 
 
@@ -431,7 +447,41 @@ def test_tiled_backward_720p_vs_cpu_oracle():
     gs, gm = run(K, smooth.to(DEV), M, target.to(DEV))
     gs_ref, gm_ref = run(R, smooth, M.cpu(), target)
     assert rel_l2(gs.cpu(), gs_ref) < 1e-4, rel_l2(gs.cpu(), gs_ref)
-    assert rel_l2(gm.cpu(), gm_ref) < 1e-3, rel_l2(gm.cpu(), gm_ref)  # CPU-vs-CUDA reference itself: ~1e-4
+    # against the CPU run the bound is the reference's own CPU-vs-CUDA gap (base grid and bmm differ by an ulp between the
+    # backends); the north_star tolerance is asserted against the SAME-DEVICE reference in the next test
+    assert rel_l2(gm.cpu(), gm_ref) < 5e-4, rel_l2(gm.cpu(), gm_ref)
+
+
+@pytest.mark.parametrize("images", ["bandlimited", "white"])
+def test_gradients_match_the_same_device_reference_at_the_cfg4_shape(images):
+    """north_star: within 1e-4 rel of the reference's own grid_sample path.  The reference composition (oracle/kornia_restated.py,
+    the ATen calls the reference issues) runs on the SAME GPU, cuDNN off, at BASELINE.json configs[3]'s shape (reduced batch); d/dsrc
+    and d/dH through both, for the well-conditioned band-limited loss and for a white-noise cotangent.  (tests/geometry/transform/
+    test_imgwarp.py:548-555 skips d/dH altogether; measured here: ~5e-8 and ~1e-6.)"""
+    import bench
+
+    H, W, B = 720, 1280, 4
+    M = _bench_homographies(B, H, W, 7).to(DEV)
+    shape = (B, 3, H, W)
+    if images == "white":
+        src, cot = torch.rand(shape, device=DEV), torch.randn(shape, device=DEV)
+        loss = lambda out: (out * cot).sum()  # noqa: E731
+    else:
+        src, target = bench.bandlimited(shape, DEV, 12), bench.bandlimited(shape, DEV, 13)
+        loss = lambda out: ((out - target) ** 2).mean()  # noqa: E731
+
+    def run(mod):
+        s, m = src.clone().requires_grad_(True), M.clone().requires_grad_(True)
+        out = mod.warp_perspective(s, m, (H, W))
+        return (out.detach(),) + torch.autograd.grad(loss(out), [s, m])
+
+    with torch.backends.cudnn.flags(enabled=False):
+        want = run(R)
+    got = run(K)
+    assert torch.equal(got[0], want[0]), "the forward is bit-identical to the same-device reference"
+    assert rel_l2(got[1], want[1]) < 1e-5, rel_l2(got[1], want[1])   # d/dsrc: only the order of the adds differs
+    for b in range(B):
+        assert rel_l2(got[2][b], want[2][b]) < 1e-4, (b, rel_l2(got[2][b], want[2][b]))  # d/dH per sample
 
 
 @pytest.mark.parametrize("border", ["constant", "reflect", "replicate"])
@@ -537,4 +587,4 @@ def test_tiled_backward_shared_affine_matrix():
     assert rel_l2(gs, gs_ref) < 2e-6 and rel_l2(ga, ga_ref) < 1e-4
     s, a = src.cpu().requires_grad_(True), A.cpu().requires_grad_(True)
     gs_cpu, ga_cpu = torch.autograd.grad(R.warp_affine(s, a, (H, W)), [s, a], grad_outputs=cot.cpu())
-    assert rel_l2(gs.cpu(), gs_cpu) < 1e-4 and rel_l2(ga.cpu(), ga_cpu) < 1e-3
+    assert rel_l2(gs.cpu(), gs_cpu) < 1e-4 and rel_l2(ga.cpu(), ga_cpu) < 5e-4  # vs CPU: bounded by the reference's own CPU-vs-CUDA gap

@@ -329,3 +329,30 @@ def test_fast_filter_backward_ssim_loss_and_goldens():
         for key, want in outs.items():
             if key != "cot":
                 assert rel_l2(got[key].cpu(), want) < 1e-4, (name, key)
+
+
+# ------------------------------------------------------------------------------------------ more planes than one launch takes
+def test_feature_map_sized_plane_counts():
+    """B * C above the 65535-plane limit of one filter launch (e.g. B=256, C=256 feature maps): served by several
+    launches over batch slices, per-sample kernels keep cycling, the kernel gradient folds the slices."""
+    from oracle import kornia_restated as R
+
+    B, C, H, W = 300, 256, 8, 12
+    x = torch.rand(B, C, H, W, device=DEV)
+    k1 = torch.randn(1, 3, 3, device=DEV)
+    kb = torch.randn(B, 3, 3, device=DEV)
+    for kern in (k1, kb):
+        got = K.filter2d(x, kern)
+        want = torch.cat([R.filter2d(x[i:i + 50], kern if kern.shape[0] == 1 else kern[i:i + 50]) for i in range(0, B, 50)])
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+    kx, ky = torch.randn(1, 5, device=DEV), torch.randn(B, 5, device=DEV)
+    got = K.filter2d_separable(x, kx, ky)
+    want = torch.cat([R.filter2d_separable(x[i:i + 50], kx, ky[i:i + 50]) for i in range(0, B, 50)])
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+    xs = x[:, :, :6, :8].contiguous().requires_grad_(True)
+    kg = torch.randn(2, 3, 3, device=DEV, requires_grad=True)   # two kernels cycling over 300 samples
+    gx, gk = torch.autograd.grad(K.filter2d(xs, kg).square().sum(), [xs, kg])
+    xr, kr = xs.detach().clone().requires_grad_(True), kg.detach().clone().requires_grad_(True)
+    gx_r, gk_r = torch.autograd.grad(R.filter2d(xr, kr).square().sum(), [xr, kr])
+    torch.testing.assert_close(gx, gx_r, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gk, gk_r, rtol=1e-3, atol=1e-2)

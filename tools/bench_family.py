@@ -80,9 +80,9 @@ with torch.no_grad():
     line("points -> H -> warp_perspective", lambda: K.warp_perspective(x, KT.get_perspective_transform(quad, quad_to), (H, W)),
          lambda: R.warp_perspective(x, R.perspective_from_points(quad, quad_to), (H, W)), 8)
     fused_h = t(lambda: KT.get_perspective_transform(quad, quad_to), 50)
-    os.environ["KORNIA_B200_TORCH_PRELUDE"] = "1"
+    K.config.set("torch_prelude", 1)
     torch_h = t(lambda: KT.get_perspective_transform(quad, quad_to), 20)
-    del os.environ["KORNIA_B200_TORCH_PRELUDE"]
+    K.config.reset()
     print(f"get_perspective_transform alone (B={B}): fused {fused_h * 1e3:.1f} us, torch op sequence {torch_h * 1e3:.1f} us", flush=True)
     rows.append(dict(op="get_perspective_transform", fused_us=round(fused_h * 1e3, 1), torch_us=round(torch_h * 1e3, 1)))
 out = os.path.join(ROOT, "gpurun_out", "family_bench.json")
