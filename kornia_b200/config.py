@@ -8,7 +8,7 @@ to run a kernel against the one it stands in for.
 
 Device-side (forwarded to the C library): ``tma`` (TMA-tiled warp / remap / backward kernels; off = generic per-pixel
 kernels), ``tiled_filter`` (shared-memory filter kernels; off = generic), ``square_tiles`` (second forward tile shape for
-rotated samples), ``sep_vwalk`` (band-walking separable filter: -1 auto = 13 taps and more, 0 never, 1 whenever it
+rotated samples), ``sep_vwalk`` (band-walking separable filter: -1 auto = 11 taps and more, 0 never, 1 whenever it
 applies), ``tiled_gradient``, ``u8_tiled`` (staged-window uint8 ingest warp; off = per-tap kernel).
 Host-side: ``fused_pyrdown`` (5x5 blur + 2x decimation in one kernel), ``fused_undistort`` (lens model evaluated inside
 the sampling kernel), ``fast_filter_bwd`` (input gradient of the separable filter through the one-pass forward kernel),

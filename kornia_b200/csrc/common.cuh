@@ -81,7 +81,7 @@ enum Option {
   OPT_TMA,             // TMA-tiled warp / remap / backward kernels (off: the generic per-pixel kernels)
   OPT_TILED_FILTER,    // shared-memory filter kernels (off: filter_generic.cuh)
   OPT_SQUARE_TILES,    // second tile shape of the forward warp for rotated samples
-  OPT_SEP_VWALK,       // band-walking separable filter: -1 auto (13 taps and more), 0 never, 1 whenever it applies
+  OPT_SEP_VWALK,       // band-walking separable filter: -1 auto (11 taps and more), 0 never, 1 whenever it applies
   OPT_TILED_GRADIENT,  // shared-memory derivative stencils (off: gradient.cuh)
   OPT_U8_TILED,        // staged-window uint8 ingest warp (off: per-tap kernel)
   OPT_COUNT

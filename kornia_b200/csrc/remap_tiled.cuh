@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(256, LENS ? 3 : 4) remap_tiled_kernel(const __
         ix = fminf(Wm1, fmaxf(ix, 0.f));
         iy = fminf(Hm1, fmaxf(iy, 0.f));
       }
+      ix = interior_reflection<PAD, ALIGN>(ix);  // the window test and the taps below see the coordinate reflect_coord returns
+      iy = interior_reflection<PAD, ALIGN>(iy);
       float* o = obase + (size_t)y * p.w + x;
       if (ix >= wlx && ix < whx && iy >= wly && iy < why) {
         const float tX = __fadd_rd(ix, FLOOR_MAGIC), tY = __fadd_rd(iy, FLOOR_MAGIC);

@@ -14,7 +14,11 @@ template <typename T>
 __device__ __forceinline__ T unnormalize(T g, int size, bool align) {
   using R = RN<T>;
   if (align) return R::mul(R::mul(R::add(g, T(1)), T(0.5)), T(size - 1));
-  return R::mul(R::sub(R::mul(R::add(g, T(1)), T(size)), T(1)), T(0.5));
+  // ((g + 1) * size - 1) / 2 as ATen's CUDA kernel evaluates it: nvcc contracts the product and the subtraction into one FMA
+  // there (cuda/GridSampler.cuh is built with -fmad=true), so the same-device reference is reproduced bit for bit
+  // (tests/test_parity_gpu.py::test_warp_forward_fp32_equals_the_same_device_reference); torch's CPU kernel rounds the product
+  // separately -- a one-ulp difference in the coordinate, inside the reference's own CPU-vs-CUDA gap.
+  return R::mul(R::fma(R::add(g, T(1)), T(size), T(-1)), T(0.5));
 }
 
 template <typename T>
@@ -32,6 +36,16 @@ __device__ __forceinline__ T reflect_coord(T c, int twice_low, int twice_high) {
   const T extra = R::fmod(c, span);
   const int flips = static_cast<int>(R::floor(R::div(c, span)));
   return (flips % 2 == 0) ? R::add(extra, lo) : R::add(R::sub(span, extra), lo);
+}
+
+// Inside the image the reflection of GridSampler.h:89-105 is the identity -- up to its own rounding: with align_corners=False
+// the coordinate makes a round trip through the half-pixel offset (|c - (-0.5)|, fmod by the span, + (-0.5)).  The tiled
+// kernels restrict their fast path to interior pixels under 'reflection' and apply exactly this round trip there, so that they
+// agree with reflect_coord (and with ATen) bit for bit.
+template <int PAD, bool ALIGN>
+__device__ __forceinline__ float interior_reflection(float c) {
+  if (PAD == KB200_REFLECTION && !ALIGN) return RN<float>::add(RN<float>::sub(c, -0.5f), -0.5f);
+  return c;
 }
 
 // values that cannot be an index (NaN, +-inf, beyond int range) become -100: out of bounds

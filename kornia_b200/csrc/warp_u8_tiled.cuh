@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(256, KIND == U8_KIND_LENS ? 3 : 4) warp_u8_til
         ix = fminf(Wm1, fmaxf(ix, 0.f));
         iy = fminf(Hm1, fmaxf(iy, 0.f));
       }
+      ix = interior_reflection<PAD, ALIGN>(ix);  // the window test and the taps below see the coordinate reflect_coord returns
+      iy = interior_reflection<PAD, ALIGN>(iy);
       float* o = obase + (size_t)y * p.w + x;
 #ifdef KB200_HOST_EMU
       ++((ix >= wlx && ix < whx && iy >= wly && iy < why) ? u8t_fast_pixels : u8t_exact_pixels);

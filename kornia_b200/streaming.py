@@ -21,7 +21,7 @@ from typing import Callable, Optional, Sequence
 
 import torch
 
-__all__ = ["bind_to_device_numa_node", "device_numa_node", "pinned_empty", "HostPipeline", "apply_host", "warp_perspective_host",
+__all__ = ["bind_to_device_numa_node", "device_numa_node", "pinned_empty", "HostPipeline", "apply_host", "join", "warp_perspective_host",
            "host_ring_samples"]
 
 
@@ -186,10 +186,19 @@ class HostPipeline:
             self._ev = [[torch.cuda.Event() for _ in range(self.nbuf)] for _ in range(3)]
         return st
 
-    def run(self, fn: Callable[..., torch.Tensor], inputs: Sequence[torch.Tensor], out: torch.Tensor, batch: Optional[int] = None) -> torch.Tensor:
+    def join(self) -> None:
+        """Make the caller's current stream wait for everything the pipeline has queued (copies included)."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_k, self.s_out):
+            cur.wait_stream(s)
+
+    def run(self, fn: Callable[..., torch.Tensor], inputs: Sequence[torch.Tensor], out: torch.Tensor, batch: Optional[int] = None,
+            join: bool = True) -> torch.Tensor:
         """One pass over ``batch`` samples (default: the length of the host tensors).  ``inputs``: host tensors sharing dim 0;
         when they are shorter than ``batch`` they are a pinned ring that is read (and ``out`` written) cyclically -- the ring
-        length must then be a whole number of chunks."""
+        length must then be a whole number of chunks.  ``join=False`` leaves the caller's stream free: back-to-back passes then
+        overlap (the first copies of pass n+1 run under the last kernels and copies of pass n; slots are ordered by events
+        across passes) and the caller calls :meth:`join` once at the end."""
         hb = inputs[0].shape[0]
         batch = hb if batch is None else int(batch)
         if batch > hb and hb % self.chunk != 0:
@@ -198,10 +207,13 @@ class HostPipeline:
             raise ValueError("inputs and out must share their first dimension")
         stage = self._staging(inputs)
         ev_in, ev_k, ev_out = self._ev
-        results = [None] * self.nbuf
+        if getattr(self, "_results", None) is None:
+            self._results = [None] * self.nbuf  # kept across passes: a result may still be on its way out when the next pass starts
+        results = self._results
         cur = torch.cuda.current_stream(self.device)
-        for s in (self.s_in, self.s_k, self.s_out):
-            s.wait_stream(cur)
+        # only the compute stream depends on the caller's stream (device tensors the caller produced, e.g. the matrices); the
+        # copies read / write host memory and are ordered among themselves by the slot events
+        self.s_k.wait_stream(cur)
         for i, b0 in enumerate(range(0, batch, self.chunk)):
             j = i % self.nbuf
             n = min(self.chunk, batch - b0)
@@ -219,9 +231,10 @@ class HostPipeline:
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_k[j])
                 out[h0:h0 + n].copy_(results[j], non_blocking=True)
+                results[j].record_stream(self.s_out)  # allocated on the compute stream, read here: tell the caching allocator
                 ev_out[j].record(self.s_out)
-        for s in (self.s_in, self.s_k, self.s_out):
-            cur.wait_stream(s)
+        if join:
+            self.join()
         return out
 
 
@@ -236,8 +249,13 @@ def _pipeline(device, chunk: int) -> HostPipeline:
     return p
 
 
+def join(device="cuda", chunk: int = 16) -> None:
+    """Wait (on the caller's current stream) for the passes issued with ``join=False`` on this device's pipeline."""
+    _pipeline(device, chunk).join()
+
+
 def apply_host(fn: Callable[..., torch.Tensor], inputs: Sequence[torch.Tensor], out: torch.Tensor, device="cuda", chunk: int = 16,
-               logical_batch: Optional[int] = None, synchronize: bool = True) -> torch.Tensor:
+               logical_batch: Optional[int] = None, synchronize: bool = True, join: bool = True) -> torch.Tensor:
     """``out[b] = fn(inputs[b]...)`` for host tensors, chunked and pipelined on ``device`` (see :class:`HostPipeline`).
     ``logical_batch`` > len(inputs[0]) streams that many samples through the (shorter) host ring cyclically -- what a
     benchmark or a producer/consumer loop does when the whole batch cannot be page-locked at once."""
@@ -245,7 +263,7 @@ def apply_host(fn: Callable[..., torch.Tensor], inputs: Sequence[torch.Tensor], 
         if t.is_cuda:
             raise RuntimeError("kornia_b200.streaming: inputs and out are HOST tensors; call the op directly for device tensors")
     pipe = _pipeline(device, chunk)
-    pipe.run(fn, inputs, out, batch=logical_batch)
+    pipe.run(fn, inputs, out, batch=logical_batch, join=join or synchronize)
     if synchronize:
         torch.cuda.current_stream(pipe.device).synchronize()
     return out
@@ -253,7 +271,8 @@ def apply_host(fn: Callable[..., torch.Tensor], inputs: Sequence[torch.Tensor], 
 
 def warp_perspective_host(src: torch.Tensor, M: torch.Tensor, dsize: tuple[int, int], mode: str = "bilinear", padding_mode: str = "zeros",
                           align_corners: bool = True, fill_value: Optional[torch.Tensor] = None, *, out: Optional[torch.Tensor] = None,
-                          device="cuda", chunk: int = 16, logical_batch: Optional[int] = None, synchronize: bool = True) -> torch.Tensor:
+                          device="cuda", chunk: int = 16, logical_batch: Optional[int] = None, synchronize: bool = True,
+                          join: bool = True) -> torch.Tensor:
     """``warp_perspective`` (imgwarp.py:69 semantics) for a batch in host memory: ``src`` (B,C,H,W) fp32 host tensor (pinned
     for full speed: :func:`pinned_empty`) or interleaved uint8 (B,H,W,C) decoder frames (3 B/pixel over PCIe instead of 12,
     converted and warped in one kernel: ``warp_perspective_from_uint8``); ``M`` (B,3,3) on the host or already on the
@@ -276,4 +295,4 @@ def warp_perspective_host(src: torch.Tensor, M: torch.Tensor, dsize: tuple[int, 
     def step(chunk_src, b0, b1):
         return op(chunk_src, M_dev[b0:b1], dsize, mode, padding_mode, align_corners, fill_value)
 
-    return apply_host(step, [src], out, device=dev, chunk=chunk, logical_batch=logical_batch, synchronize=synchronize)
+    return apply_host(step, [src], out, device=dev, chunk=chunk, logical_batch=logical_batch, synchronize=synchronize, join=join)

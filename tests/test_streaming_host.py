@@ -71,6 +71,13 @@ def test_host_pipeline_equals_the_direct_call():
     out = S.pinned_empty((16, 3, 40, 64), torch.float32, 0)
     S.warp_perspective_host(ring, M[:16].repeat(3, 1, 1), (40, 64), out=out, chunk=8, logical_batch=48)
     assert torch.equal(out, want[:16])
+    # back-to-back passes without joining the caller's stream in between (what a stream of batches does), joined once at the end
+    outs = [S.pinned_empty((B, 3, 40, 64), torch.float32, 0) for _ in range(3)]
+    for o in outs:
+        S.warp_perspective_host(pinned, M, (40, 64), out=o, chunk=8, synchronize=False, join=False)
+    S.join("cuda", 8)
+    torch.cuda.current_stream().synchronize()
+    assert all(torch.equal(o, want) for o in outs)
     # decoder bytes in: 3 B/pixel over PCIe, converted and warped in one kernel
     frames = (torch.rand(B, 48, 80, 3, generator=g) * 255).to(torch.uint8)
     ref = K.geometry.transform.warp_perspective_from_uint8(frames.cuda(), M.cuda(), (40, 64)).cpu()
