@@ -43,6 +43,15 @@ BYTES_PER_PIX = 24.0  # algorithmic: 3 channels x 4 B read + 3 x 4 B written per
 METRIC = "Mpix/s warp_perspective Bx3x1080x1920 fwd bilinear fp32"
 
 
+def headline_config(B: int, world: int) -> dict:
+    """The `config` both arms print for the headline (BASELINE.json configs[1]); the reference arm times a per-step SAMPLE of this
+    configuration (stated in its `cpu_baseline.sample`), the metric is per pixel."""
+    return {"workload": f"warp_perspective fwd B={B}x3x1080x1920 per GPU, bilinear, zeros, align_corners=True (BASELINE.json configs[1])",
+            "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no data-path collective",
+            "l2": "inputs (6.37 GB/GPU) exceed the 126 MB L2; no explicit flush",
+            "homographies": "corner quad jittered by 8*randn px (benchmarks/geometry/flagship.py recipe), seed 1000+rank"}
+
+
 # ------------------------------------------------------------------------------------------ inputs
 def perspective_from_quads(src_q: torch.Tensor, dst_q: torch.Tensor) -> torch.Tensor:
     """DLT: the (B,3,3) homography mapping 4 source corners to 4 destination corners (what
@@ -189,10 +198,10 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"warp_perspective fwd B={args.batch}x3x1080x1920 bilinear zeros align_corners=True",
-                   "per_step_sample": f"B={sample_b} of the batch (CPU per-image throughput is batch independent)"},
+        "config": headline_config(args.batch, args.gpus),
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                         "sample": f"B={sample_b}x3x1080x1920 per step, torch CPU ops (oracle/kornia_restated.py), {cores} of {os.cpu_count()} threads (best of a calibration)"},
+                         "sample": f"each step = B={sample_b}x3x1080x1920 of the configuration's batch (CPU per-image throughput is batch independent), torch CPU ops "
+                                   f"(oracle/kornia_restated.py: the reference's ATen call sequence), {cores} of {os.cpu_count()} threads (best of a calibration)"},
         "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -346,9 +355,11 @@ def host_ring_samples(B: int, chunk: int, available_bytes=None, local_ranks=None
     return ring(B, chunk, 2 * C_IMG * H_IMG * W_IMG * 4, available_bytes, local_ranks)
 
 
-def e2e_run(K, M_dev, B, steps, warmup, chunk, dev):
+def e2e_run(K, M_dev, B, steps, warmup, chunk, dev, uint8_frames=False):
     """Host-buffer throughput through the library's own host pipeline (kornia_b200.streaming.warp_perspective_host: pinned
-    src -> device -> warp -> pinned dst, chunked over 3 streams, the process bound to the GPU's NUMA node)."""
+    src -> device -> warp -> pinned dst, chunked over 3 streams, the process bound to the GPU's NUMA node).  ``uint8_frames``:
+    the source is what a decoder delivers -- interleaved uint8 (B,H,W,3), 3 bytes per pixel over PCIe instead of 12 -- converted
+    and warped in one kernel (warp_perspective_from_uint8); the fp32 result comes back as before."""
     from kornia_b200 import streaming
 
     n_el = B * C_IMG * H_IMG * W_IMG
@@ -358,13 +369,20 @@ def e2e_run(K, M_dev, B, steps, warmup, chunk, dev):
     # of whole chunks instead: the bytes crossing PCIe per step are the same, the note says which form ran.
     HB = host_ring_samples(B, chunk)
     try:
-        src_h = streaming.pinned_empty((HB, C_IMG, H_IMG, W_IMG), torch.float32, dev.index)
+        if uint8_frames:
+            src_h = streaming.pinned_empty((HB, H_IMG, W_IMG, C_IMG), torch.uint8, dev.index)
+        else:
+            src_h = streaming.pinned_empty((HB, C_IMG, H_IMG, W_IMG), torch.float32, dev.index)
         dst_h = streaming.pinned_empty((HB, C_IMG, H_IMG, W_IMG), torch.float32, dev.index)
     except RuntimeError as e:  # not enough lockable host memory
         return None, f"pinned allocation failed: {e}"
     # cheap deterministic fill (content does not affect timing); touching every page also places it
-    src_h.view(-1)[: 1 << 20].uniform_()
-    src_h.view(-1)[1 << 20:] = 0.5
+    if uint8_frames:
+        src_h.view(-1)[: 1 << 20].random_(0, 256)
+        src_h.view(-1)[1 << 20:] = 127
+    else:
+        src_h.view(-1)[: 1 << 20].uniform_()
+        src_h.view(-1)[1 << 20:] = 0.5
     dst_h.zero_()
 
     def one_step():
@@ -388,8 +406,9 @@ def e2e_run(K, M_dev, B, steps, warmup, chunk, dev):
     ms = t0.elapsed_time(t1) / steps
     del src_h, dst_h
     host = "whole batch pinned" if HB == B else f"pinned ring of {HB} samples reused {B / HB:.1f}x per step (host memory per local rank)"
+    h2d = n_el * (1 if uint8_frames else 4)
     return ms, (f"kornia_b200.streaming.warp_perspective_host: pinned host buffers ({host}), chunk={chunk} samples, 3 streams (H2D / kernel / D2H), "
-                f"{n_el * 4} B each way per step; NUMA binding {numa}")
+                f"{h2d} B in / {n_el * 4} B out per step; NUMA binding {numa}")
 
 
 def max_over_ranks_or_none(dist, ms, note, device):
@@ -467,6 +486,11 @@ def run_ours(args) -> None:
     if dist is not None:
         e2e_ms, e2e_note = max_over_ranks_or_none(dist, e2e_ms, e2e_note, dev)
     barrier()
+    # the same step fed with decoder bytes: context for the e2e number, not the headline (a different wire format)
+    u8_ms, u8_note = e2e_run(K, M, B, steps=3, warmup=1, chunk=args.e2e_chunk, dev=dev, uint8_frames=True)
+    if dist is not None:
+        u8_ms, u8_note = max_over_ranks_or_none(dist, u8_ms, u8_note, dev)
+    barrier()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -505,10 +529,7 @@ def run_ours(args) -> None:
         "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"warp_perspective fwd B={B}x3x1080x1920 per GPU, bilinear, zeros, align_corners=True (BASELINE.json configs[1])",
-                   "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no data-path collective",
-                   "l2": "inputs (6.37 GB/GPU) exceed the 126 MB L2; no explicit flush", "kernel_variant": variant,
-                   "homographies": "corner quad jittered by 8*randn px (benchmarks/geometry/flagship.py recipe), seed 1000+rank"},
+        "config": headline_config(B, world), "kernel_variant": variant,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel_ms": k_ms, "kernel_launches_timed": len(kern_ms), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_PIX * B * H_IMG * W_IMG},
@@ -516,6 +537,9 @@ def run_ours(args) -> None:
         "e2e": ({"value": pix_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": bytes_step,
                  "d2h_bytes_per_step": bytes_step, "ms_per_step": e2e_ms, "note": e2e_note}
                 if e2e_ms is not None else {"value": None, "unit": "Mpix/s", "note": e2e_note}),
+        "e2e_uint8_frames": ({"value": pix_step / (u8_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": bytes_step // 4,
+                              "d2h_bytes_per_step": bytes_step, "ms_per_step": u8_ms, "note": u8_note}
+                             if u8_ms is not None else {"value": None, "unit": "Mpix/s", "note": u8_note}),
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "checksum": checksum,
