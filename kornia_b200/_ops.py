@@ -123,6 +123,18 @@ def _direct(*tensors: Optional[torch.Tensor]) -> bool:
     return True
 
 
+_HALF = (torch.float16, torch.bfloat16)
+
+
+def _half_passthrough(fn, image: torch.Tensor, others: Sequence[Optional[torch.Tensor]], *rest):
+    """fp16 / bf16 images (the pass-through dtypes of the reference's test matrix, testing/base.py:35-36; not a BASELINE
+    configuration): the kernels compute in fp32 -- operands are widened, the result is narrowed back to the image's dtype;
+    autograd flows through the casts.  Costs two conversion passes; the arithmetic is at least as accurate as the reference's
+    half-precision composition."""
+    wide = [None if t is None else (t.float() if t.is_floating_point() else t) for t in others]
+    return fn(image.float(), *wide, *rest).to(image.dtype)
+
+
 def _autograd(name: str, backward, setup_context) -> None:
     torch.library.register_autograd(f"{NS}::{name}", backward, setup_context=setup_context, lib=_library)
 
@@ -236,6 +248,10 @@ _autograd("warp_fwd", _warp_backward, _warp_setup)
 
 
 def warp(src, m, bx, by, fill, h, w, projective, interp, pad, align):
+    if src.dtype in _HALF:
+        if m.dtype != src.dtype:
+            raise RuntimeError(f"expected the transformation matrix to have the same dtype as the image, but got {m.dtype} and {src.dtype}")
+        return _half_passthrough(warp, src, (m, bx, by, fill), h, w, projective, interp, pad, align)
     if _direct(src, m, fill):
         return _warp_fwd_cuda(src, m, bx, by, fill, int(h), int(w), bool(projective), int(interp), int(pad), bool(align))
     return ops.warp_fwd(src, m, bx, by, fill, int(h), int(w), bool(projective), int(interp), int(pad), bool(align))
@@ -382,6 +398,8 @@ _autograd("remap_fwd", _remap_backward, _remap_setup)
 
 
 def remap(image, map_x, map_y, normalized, interp, pad, align):
+    if image.dtype in _HALF:
+        return _half_passthrough(remap, image, (map_x, map_y), normalized, interp, pad, align)
     if _direct(image, map_x, map_y):
         return _remap_fwd_cuda(image, map_x, map_y, bool(normalized), int(interp), int(pad), bool(align))
     return ops.remap_fwd(image, map_x, map_y, bool(normalized), int(interp), int(pad), bool(align))
@@ -532,6 +550,8 @@ _autograd("filter2d_fwd", _filter2d_backward, _filter2d_setup)
 
 
 def filter2d(x, kernel, border, same):
+    if x.dtype in _HALF:
+        return _half_passthrough(filter2d, x, (kernel,), border, same)
     if _direct(x, kernel):
         return _filter2d_fwd_cuda(x, kernel, int(border), bool(same))
     return ops.filter2d_fwd(x, kernel, int(border), bool(same))
@@ -612,6 +632,8 @@ _autograd("sepfilter_fwd", _sepfilter_backward, _sepfilter_setup)
 
 
 def sepfilter(x, kx, ky, border, same):
+    if x.dtype in _HALF:
+        return _half_passthrough(sepfilter, x, (kx, ky), border, same)
     if _direct(x, kx, ky):
         return _sepfilter_fwd_cuda(x, kx, ky, int(border), bool(same))
     return ops.sepfilter_fwd(x, kx, ky, int(border), bool(same))

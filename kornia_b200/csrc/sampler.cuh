@@ -48,6 +48,24 @@ __device__ __forceinline__ float interior_reflection(float c) {
   return c;
 }
 
+// reflect_coord + clip_coord ('reflection' of a bilinear / nearest coordinate, GridSampler.h:89-105,143-160) without fmod / div for
+// coordinates within one span of the image -- which is every pixel of a border tile: |c - lo| < span has flips = 0 and
+// fmod = identity, span <= |c - lo| < 2 span has flips = 1 and fmod(a, span) = a - span EXACTLY (Sterbenz), anything further
+// out takes reflect_coord itself.  Bit-identical to clip_coord(reflect_coord(...)) for every input (tools/hostemu checks it).
+template <bool ALIGN>
+__device__ __forceinline__ float reflect_clip_fast(float c, int size) {
+  using R = RN<float>;
+  const int tl = ALIGN ? 0 : -1, th = ALIGN ? 2 * (size - 1) : 2 * size - 1;
+  if (tl == th) return 0.f;
+  const float lo = (float)tl * 0.5f, span = (float)(th - tl) * 0.5f;
+  const float a = R::abs(R::sub(c, lo));
+  float r;
+  if (a < span) r = R::add(a, lo);
+  else if (a < 2.f * span) r = R::add(R::sub(span, R::sub(a, span)), lo);
+  else r = reflect_coord(c, tl, th);
+  return clip_coord(r, size);
+}
+
 // values that cannot be an index (NaN, +-inf, beyond int range) become -100: out of bounds
 template <typename T>
 __device__ __forceinline__ T guard_index(T c) {

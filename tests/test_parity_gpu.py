@@ -95,11 +95,9 @@ def test_warp_grads_match_reference(name):
         assert rel_l2(g, want) < 1e-4, (key, rel_l2(g, want))
 
 
-@pytest.mark.parametrize("name", GRAD_WARP[::3])
+@pytest.mark.parametrize("name", [n for n in GRAD_WARP[::3] if WARP.case(n)[1]["mode"] != "nearest"])  # nearest has no coordinate gradient
 def test_warp_grads_fp64_match_oracle(name):
     op, kw, ins, _ = WARP.case(name)
-    if kw["mode"] == "nearest":
-        pytest.skip("tie flips")
     got = run_case(K, op, kw, ins, device=DEV, dtype=torch.float64)
     want = run_case(R, op, kw, ins, device=DEV, dtype=torch.float64)  # same device: same fp32 base grid
     for key in want:
@@ -556,10 +554,10 @@ def test_empty_batch_and_huge_separable_kernel():
     assert rel_l2(got.cpu(), want) < 1e-5
 
 
-def test_second_device_if_present():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("single GPU")
-    d1 = torch.device("cuda:1")
+def test_last_visible_device():
+    """Device placement follows the tensors, not the current device: runs on the LAST visible GPU (cuda:1.. on a multi-GPU box;
+    on a single-GPU box that is cuda:0 addressed explicitly while the current device stays the default)."""
+    d1 = torch.device("cuda", torch.cuda.device_count() - 1)
     x = torch.rand(2, 3, 64, 128, device=d1)
     M = torch.eye(3, device=d1)[None].repeat(2, 1, 1)
     M[:, 0, 2] = 2.0

@@ -208,3 +208,32 @@ def test_inference_then_training_on_the_device():
     s = src.clone().requires_grad_(True)
     (K.warp_perspective(s, M, (24, 40)).sum() + K.gaussian_blur2d(s, (7, 7), (1.2, 1.2)).sum()).backward()
     assert torch.isfinite(s.grad).all()
+
+
+@gpu
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_images_pass_through(dtype):
+    """fp16 / bf16 are in the reference's test matrix (testing/base.py:35-36) though in no BASELINE configuration: the kernels
+    compute in fp32 and hand back the image's dtype.  Against the reference composition in the same half precision on the same
+    GPU (its coordinates are rounded to half precision, so the comparison is half-grade) and against this library's fp32 result."""
+    from oracle import kornia_restated as R
+
+    g = torch.Generator().manual_seed(5)
+    src32 = torch.rand(2, 3, 24, 32, generator=g).cuda()
+    M32 = (torch.eye(3)[None] + 0.02 * torch.randn(2, 3, 3, generator=g) * torch.tensor([[1, 1, 5.0], [1, 1, 5.0], [1e-3, 1e-3, 0]])).cuda()
+    src, M = src32.to(dtype), M32.to(dtype)
+    tol = dict(rtol=0, atol=0.02 if dtype == torch.float16 else 0.12)
+    out = K.warp_perspective(src, M, (20, 28))
+    assert out.dtype == dtype and out.shape == (2, 3, 20, 28)
+    torch.testing.assert_close(out.float(), K.warp_perspective(src.float(), M.float(), (20, 28)), **tol)
+    torch.testing.assert_close(out.float(), R.warp_perspective(src, M, (20, 28)).float(), **tol)
+    blur = K.gaussian_blur2d(src, (5, 5), (1.2, 1.2))
+    assert blur.dtype == dtype
+    torch.testing.assert_close(blur.float(), K.gaussian_blur2d(src.float(), (5, 5), (1.2, 1.2)), rtol=0, atol=0.01)
+    k = torch.rand(1, 3, 3, device="cuda", dtype=dtype)
+    assert K.filter2d(src, k).dtype == dtype
+    mx = (torch.rand(2, 20, 28, device="cuda") * 30).to(dtype)
+    assert K.remap(src, mx, mx * 0.7).dtype == dtype
+    s = src.clone().requires_grad_(True)
+    K.warp_perspective(s, M, (20, 28)).float().sum().backward()
+    assert s.grad is not None and s.grad.dtype == dtype

@@ -81,14 +81,14 @@ def test_tiled_sobel_bit_identical_and_golden(shape):
 
 
 # ------------------------------------------------------------------------------------------ band-walking separable filter
-@pytest.mark.parametrize("border", ["reflect", "replicate", "constant"])
-@pytest.mark.parametrize("ksize", [3, 5, 11, 17])
-@pytest.mark.parametrize("shape", [(2, 3, 70, 132), (1, 1, 32, 128), (3, 2, 33, 4), (1, 2, 97, 260), (1, 1, 6, 8), (2, 3, 1080, 1920)])
+_VWALK_SHAPES = [(2, 3, 70, 132), (1, 1, 32, 128), (3, 2, 33, 4), (1, 2, 97, 260), (1, 1, 6, 8), (2, 3, 1080, 1920)]
+
+
+@pytest.mark.parametrize("border,ksize,shape", [(b, k, s) for b in ("reflect", "replicate", "constant") for k in (3, 5, 11, 17) for s in _VWALK_SHAPES
+                                                if b == "constant" or min(s[-2:]) > k // 2])  # a fold needs an image larger than the half-width
 def test_band_walk_separable_filter_bit_identical(border, ksize, shape):
     """sepfilter_vwalk_kernel (KB200_SEP_VWALK=1) == sepfilter_tiled_kernel, bit for bit: same taps, same FMA order, the
     vertical fold applied to row-filtered rows instead of input rows.  Per-sample taps exercise the b % Bk indexing."""
-    if border != "constant" and min(shape[-2:]) <= ksize // 2:
-        pytest.skip("fold distance exceeds the image")
     g = torch.Generator().manual_seed(ksize)
     x = torch.rand(*shape, device=DEV)
     kx = torch.rand(shape[0], ksize, generator=g).to(DEV)
@@ -131,13 +131,12 @@ def test_band_walk_many_segments_and_blur_golden():
 
 
 # ------------------------------------------------------------------------------------------ band-walking SSIM
-@pytest.mark.parametrize("window", [3, 5, 7, 9, 11])
-@pytest.mark.parametrize("shape", [(2, 3, 70, 132), (1, 1, 32, 64), (3, 2, 33, 8), (1, 2, 97, 260), (1, 1, 6, 8), (1, 3, 1080, 1920)])
+@pytest.mark.parametrize("window,shape", [(w, s) for w in (3, 5, 7, 9, 11)
+                                          for s in ((2, 3, 70, 132), (1, 1, 32, 64), (3, 2, 33, 8), (1, 2, 97, 260), (1, 1, 6, 8), (1, 3, 1080, 1920))
+                                          if min(s[-2:]) > w // 2])  # a reflect fold needs an image larger than the half-window
 def test_band_walk_ssim_bit_identical(window, shape):
     """ssim_vwalk_kernel == the library's own differentiable composition (five one-pass blurs + torch elementwise ops, the path
     taken when a gradient is needed), bit for bit."""
-    if min(shape[-2:]) <= window // 2:
-        pytest.skip("reflect distance exceeds the image")
     a = torch.rand(*shape, device=DEV)
     b = (a + 0.1 * torch.randn(*shape, device=DEV)).clamp(0, 1)
     want = K.metrics.ssim(a.clone().requires_grad_(True), b, window).detach()

@@ -340,12 +340,11 @@ static void test_undistort(int B, int H, int W, bool lazy, bool strong = false) 
 
 
 // ------------------------------------------------------------------------------------------ tiled warp forward (the headline kernel)
-template <bool PROJ, int PAD, int TW, int TH, int BW, int BH, int INTERP = KB200_BILINEAR>
+template <bool PROJ, int PAD, int TW, int TH, int BW, int BH, int INTERP = KB200_BILINEAR, bool ALIGN = true>
 static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool lazy, bool tame) {
   emu::lazy_tma = lazy;
   emu::set_smem(tma_smem, sizeof(tma_smem));
   constexpr int C = 3;
-  constexpr bool ALIGN = true;
   const size_t ns = (size_t)B * C * H * W, no = (size_t)B * C * h * w;
   std::vector<float> ss, o1s, o2s;
   float* src = aligned(ss, ns);
@@ -364,7 +363,7 @@ static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool 
   TmaWarpParams p{};
   const float fillc[3] = {0.25f, 0.5f, 0.75f};
   p.src = src; p.m = m.data(); p.bx = bx.data(); p.by = by.data(); p.fill = fillc;
-  p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.align = 1; p.only_class = 0;
+  p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = B; p.align = ALIGN ? 1 : 0; p.only_class = 0;
   // oracle: the exact per-pixel path of the same header (the generic kernel's arithmetic, verified against torch on hardware)
   p.out = o2;
   for (int b = 0; b < B; ++b)
@@ -379,7 +378,7 @@ static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool 
   emu::launch(grid, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, INTERP, PAD, PROJ, ALIGN, TW, TH, BW, BH, 2>(map, p); });
   compare(std::string("warp_fwd_tma (headline, verified on hw) vs its exact path ") + (PROJ ? "projective " : "affine ") + "interp=" + std::to_string(INTERP) + " pad=" + std::to_string(PAD) + " tile " +
               std::to_string(TW) + "x" + std::to_string(TH) + " " + std::to_string(B) + "x3x" + std::to_string(H) + "x" + std::to_string(W) + " -> " + std::to_string(h) +
-              "x" + std::to_string(w) + " grid=" + std::to_string(grid) + (lazy ? " lazy" : " eager") + (tame ? " tame" : " wild"),
+              "x" + std::to_string(w) + " grid=" + std::to_string(grid) + (lazy ? " lazy" : " eager") + (tame ? " tame" : " wild") + (ALIGN ? "" : " align_corners=False"),
           o1, o2, no);
 }
 
@@ -660,7 +659,13 @@ static void fuzz(int rounds) {
   for (int r = 0; r < rounds; ++r) {
     const int H = pick(1, 110), W = 4 * pick(1, 70), planes = pick(1, 4), lazy = pick(0, 1);
     const unsigned grid = (unsigned)pick(1, 9);
-    switch (pick(0, 24)) {
+    switch (pick(0, 30)) {
+      case 25: if (H > 1) test_forward<true, KB200_REFLECTION, 64, 32, 72, 40, KB200_BILINEAR, false>(3, H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 1)); break;
+      case 26: if (H > 1) test_forward<true, KB200_FILL, 64, 32, 72, 40, KB200_BILINEAR, false>(3, H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 1)); break;
+      case 27: if (H > 1) test_forward<false, KB200_REFLECTION, 64, 32, 72, 40, KB200_NEAREST, true>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
+      case 28: if (H > 1) test_forward<true, KB200_FILL, 64, 32, 72, 40, KB200_NEAREST, false>(3, H, W, std::max(1, H - pick(0, 5)), W, grid, lazy, pick(0, 1)); break;
+      case 29: if (H > 1) test_forward<true, KB200_REFLECTION, 32, 32, 56, 56, KB200_BILINEAR, true>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
+      case 30: if (H > 1) test_forward<false, KB200_FILL, 64, 32, 72, 40, KB200_BILINEAR, true>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
       case 10: if (H > 1 && W > 1) test_filter2d<3, KB200_REFLECT>(planes, H, W, grid, lazy); break;
       case 11: if (H > 3 && W > 3) test_filter2d<7, KB200_REPLICATE>(planes, H, W, grid, lazy); break;
       case 12: test_filter2d<7, KB200_CONSTANT>(planes, H, W, grid, lazy); break;
