@@ -3,9 +3,9 @@
 
 namespace kb200 {
 
-template <int NC, int PAD, bool PROJ, bool ALIGN, bool NEED_SRC, bool NEED_M>
-static int launch2(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const CUtensorMap& mgout, const TmaBwdParams& p, cudaStream_t st) {
-  auto kern = warp_bwd_tma2<NC, PAD, PROJ, ALIGN, NEED_SRC, NEED_M>;
+template <int NC, int PAD, bool PROJ, bool ALIGN, bool NEED_SRC, bool NEED_M, bool STRIDE1>
+static int launch2s(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const CUtensorMap& mgout, const TmaBwdParams& p, cudaStream_t st) {
+  auto kern = warp_bwd_tma2<NC, PAD, PROJ, ALIGN, NEED_SRC, NEED_M, STRIDE1>;
   constexpr size_t per_warp = (size_t)NC * 72 * BWD_SH * 4;
   constexpr size_t smem = (size_t)TMA_CONSUMER_WARPS * per_warp * ((NEED_M ? 1 : 0) + (NEED_SRC ? 1 : 0)) + TMA_CONSUMER_WARPS * sizeof(uint64_t) + 64;
   static unsigned long long configured = 0;  // per instantiation, one bit per device
@@ -17,6 +17,12 @@ static int launch2(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const C
     return KB200_ECUDA;
   }
   return KB200_OK;
+}
+
+template <int NC, int PAD, bool PROJ, bool ALIGN, bool NEED_SRC, bool NEED_M>
+static int launch2(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const CUtensorMap& mgout, const TmaBwdParams& p, cudaStream_t st) {
+  if (option(OPT_BWD_STRIDE1)) return launch2s<NC, PAD, PROJ, ALIGN, NEED_SRC, NEED_M, true>(msrcwin, mgsrc, mgout, p, st);
+  return launch2s<NC, PAD, PROJ, ALIGN, NEED_SRC, NEED_M, false>(msrcwin, mgsrc, mgout, p, st);
 }
 
 int launch_warp_bwd_tma2(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const CUtensorMap& mgout, const TmaBwdParams& p, int C, int pad,

@@ -28,7 +28,12 @@
 
 namespace kb200 {
 
-template <int NC, int PAD, bool PROJ, bool ALIGN, bool NEED_SRC, bool NEED_M>
+// STRIDE1: lane <-> column (x0 + lane, x0 + 32 + lane) instead of column pairs (2 lane, 2 lane + 1).  Stride-2 lanes make every
+// strip / window access a 2-way bank conflict (half of the shared wavefronts in profiles/r2_first_bwd_ncu_digest.txt) but never
+// share a floor cell; stride-1 lanes are conflict-free but two neighbours fall into one cell wherever the map minifies.  The vote
+// stays warp-uniform: no duplicate in the instruction -> the un-predicated tap code; duplicates of multiplicity 2 -> two
+// predicated rounds (first-of-cell lanes, then second-of-cell lanes); deeper pile-ups -> the exact path.
+template <int NC, int PAD, bool PROJ, bool ALIGN, bool NEED_SRC, bool NEED_M, bool STRIDE1 = false>
 __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_constant__ CUtensorMap tmap_srcwin,
                                                                 const __grid_constant__ CUtensorMap tmap_gsrc,
                                                                 const __grid_constant__ CUtensorMap tmap_gout,
@@ -122,11 +127,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
 
       // lane <-> output columns (2 lane, 2 lane + 1): inside one instruction the lanes are two pixels apart, so
       // their floor cells are distinct whenever the source step per output pixel exceeds 1/2
-      const int x0 = tx * TW + 2 * lane;
+      constexpr int JS = STRIDE1 ? 32 : 1;  // column distance of a lane's two pixels
+      const int x0 = tx * TW + (STRIDE1 ? lane : 2 * lane);
       float bxv[NJ], cx0[NJ], cx1[NJ], cx2[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        bxv[j] = __ldg(p.bx + min(x0 + j, p.w - 1));
+        bxv[j] = __ldg(p.bx + min(x0 + JS * j, p.w - 1));
         cx0[j] = R::mul(m.m00, bxv[j]);
         cx1[j] = R::mul(m.m10, bxv[j]);
         cx2[j] = PROJ ? R::mul(m.m20, bxv[j]) : 0.f;
@@ -159,11 +165,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
 
       // upstream gradient, software-pipelined one row ahead: both columns of a lane in one 8-byte load per channel
       float2 go_next[NC];
-      {
-        const float* g0 = gbase + (size_t)min(y_base, p.h - 1) * p.w + min(x0, p.w - 2);
+      auto load_gout_row = [&](int yy, float2 (&dst)[NC]) {
+        const float* g0 = gbase + (size_t)min(yy, p.h - 1) * p.w;
+        if (STRIDE1) {  // two coalesced 128-byte rows per channel
+          const int xa = min(x0, p.w - 1), xb = min(x0 + 32, p.w - 1);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) go_next[c] = __ldg(reinterpret_cast<const float2*>(g0 + c * oplane));
-      }
+          for (int c = 0; c < NC; ++c) dst[c] = make_float2(__ldg(g0 + c * oplane + xa), __ldg(g0 + c * oplane + xb));
+        } else {        // both columns of a lane in one 8-byte load per channel
+          const float* g = g0 + min(x0, p.w - 2);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) dst[c] = __ldg(reinterpret_cast<const float2*>(g + c * oplane));
+        }
+      };
+      load_gout_row(y_base, go_next);
       if (NEED_M && win_ok) {  // warp-uniform
         tma::mbar_wait(my_full, phase);
         phase ^= 1;
@@ -180,14 +194,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
         float2 go2[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) go2[c] = go_next[c];
-        if (i + 1 < RPW) {
-          const float* g1 = gbase + (size_t)min(y + 1, p.h - 1) * p.w + min(x0, p.w - 2);
-#pragma unroll
-          for (int c = 0; c < NC; ++c) go_next[c] = __ldg(reinterpret_cast<const float2*>(g1 + c * oplane));
-        }
+        if (i + 1 < RPW) load_gout_row(y + 1, go_next);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          const int x = x0 + j;
+          const int x = x0 + JS * j;
           const bool live = y < p.h && x < p.w;  // warp-uniform in y, not in x
           const float nx = R::add(R::add(cx0[j], cy0), m.m02);
           const float ny = R::add(R::add(cx1[j], cy1), m.m12);
@@ -219,7 +229,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
           // this instruction share a floor cell -- along a row the map is monotone, so duplicates are adjacent lanes
           bool ok = live && den_ok && ix >= s_lo_x && ix < s_hi_x && iy >= s_lo_y && iy < s_hi_y;
           const int Xl = __shfl_up_sync(0xffffffffu, X, 1), Yl = __shfl_up_sync(0xffffffffu, Y, 1);
-          if (lane > 0 && Xl == X && Yl == Y) ok = false;
+          const bool same1 = lane > 0 && Xl == X && Yl == Y;  // second (or later) lane of its floor cell
+          bool two_rounds = false;
+          if (STRIDE1) {
+            const bool same2 = __shfl_up_sync(0xffffffffu, same1 ? 1 : 0, 1) != 0 && same1;  // third or later: exact path
+            if (same2) ok = false;
+            two_rounds = NEED_SRC && __any_sync(0xffffffffu, same1);
+          } else if (same1) {
+            ok = false;
+          }
           float gix = 0.f, giy = 0.f;
           if (__all_sync(0xffffffffu, ok)) {
             const float x0f = R::sub(tX, FLOOR_MAGIC), y0f = R::sub(tY, FLOOR_MAGIC);
@@ -231,7 +249,35 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
             const uint32_t cell = ((unsigned)Y * (unsigned)BW + (unsigned)X) * 4u;
             // EDGE tiles only: taps in column / row -1 are outside the image
             const bool west_in = !EDGE || !(edge_x && ix < 0.f), north_in = !EDGE || !(edge_y && iy < 0.f);
-            if (NEED_SRC) {
+            if (NEED_SRC && STRIDE1 && two_rounds) {
+              // some neighbouring lanes share a cell (the map minifies here): first-of-cell lanes, then second-of-cell lanes
+              const uint32_t a = cell + strip_base;
+#pragma unroll
+              for (int round = 0; round < 2; ++round) {
+                const bool act = (round == 0) != same1;
+                if (act && west_in && north_in) {
+#pragma unroll
+                  for (int c = 0; c < NC; ++c) tma::sts(a + c * SPLANE * 4, tma::lds(a + c * SPLANE * 4) + w_nw * go[c]);
+                }
+                __syncwarp();
+                if (act && north_in) {
+#pragma unroll
+                  for (int c = 0; c < NC; ++c) tma::sts(a + (c * SPLANE + 1) * 4, tma::lds(a + (c * SPLANE + 1) * 4) + w_ne * go[c]);
+                }
+                __syncwarp();
+                if (act && west_in) {
+#pragma unroll
+                  for (int c = 0; c < NC; ++c) tma::sts(a + (c * SPLANE + BW) * 4, tma::lds(a + (c * SPLANE + BW) * 4) + w_sw * go[c]);
+                }
+                __syncwarp();
+                if (act) {
+#pragma unroll
+                  for (int c = 0; c < NC; ++c)
+                    tma::sts(a + (c * SPLANE + BW + 1) * 4, tma::lds(a + (c * SPLANE + BW + 1) * 4) + w_se * go[c]);
+                }
+                __syncwarp();
+              }
+            } else if (NEED_SRC) {
               const uint32_t a = cell + strip_base;
               // tap by tap: lanes hit distinct cells inside one instruction; __syncwarp orders the taps
               if (west_in && north_in) {

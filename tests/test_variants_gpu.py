@@ -159,12 +159,13 @@ def test_band_walk_ssim_many_segments_and_golden():
 
 
 # ------------------------------------------------------------------------------------------ tiled backward kernels
+@pytest.mark.parametrize("stride1", [0, 1])
 @pytest.mark.parametrize("pad", ["zeros", "border"])
 @pytest.mark.parametrize("ac", [True, False])
 @pytest.mark.parametrize("C", [3, 1])
-def test_tiled_backward_matches_generic(pad, ac, C):
-    """warp_bwd_tma2 against the generic atomics kernel: same per-pixel arithmetic; d/dsrc differs only by the order of the
-    adds, d/dM by the grouping of the partial sums."""
+def test_tiled_backward_matches_generic(stride1, pad, ac, C):
+    """warp_bwd_tma2 (column-pair lanes / conflict-free stride-1 lanes, switch bwd_stride1) against the generic atomics kernel:
+    same per-pixel arithmetic; d/dsrc differs only by the order of the adds, d/dM by the grouping of the partial sums."""
     from test_parity_gpu import _bench_homographies, _generic, _wild_matrices
     from helpers import rel_l2
 
@@ -188,6 +189,7 @@ def test_tiled_backward_matches_generic(pad, ac, C):
 
         for kind in ("persp", "affine"):
             gs0, gm0 = _generic(lambda: grads(kind), check_variant=False)
+            K.config.set("bwd_stride1", stride1)
             gs2, gm2 = grads(kind)
             (gs_only,) = grads(kind, (True, False))
             (gm_only,) = grads(kind, (False, True))
@@ -202,8 +204,10 @@ def test_tiled_backward_matches_generic(pad, ac, C):
                 assert rel_l2(gm_only[b], gm2[b]) < 1e-5
 
 
-def test_tiled_backward_720p_and_goldens():
+@pytest.mark.parametrize("stride1", [0, 1])
+def test_tiled_backward_720p_and_goldens(stride1):
     """cfg4's shape at reduced batch against the reference's autograd on CPU, and every golden gradient case."""
+    K.config.set("bwd_stride1", stride1)
     from helpers import rel_l2, run_case
     from oracle import kornia_restated as R
     from test_parity_gpu import _bench_homographies

@@ -456,7 +456,8 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
     const CUtensorMap mgsrc = emu::make_map(gsrc, W, H, B * C, 72, BWD_SH, C), mgout = emu::make_map(gout, w, h, B * C, 64, 32, C);
     emu::set_smem(bwd2_smem, sizeof(bwd2_smem));
     const CUtensorMap mwin = emu::make_map(src, W, H, B * C, 72, BWD_SH, C);
-    emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true>(mwin, mgsrc, mgout, p); });
+    if (version == 2) emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true, false>(mwin, mgsrc, mgout, p); });
+    else emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true, true>(mwin, mgsrc, mgout, p); });
     exact[version] = emu_exact_path_pixels;
     gm.assign((size_t)B * 9, 0.0);
     for (size_t r = 0; r < rows; ++r)
@@ -470,6 +471,7 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
   float* g2 = aligned(g2s, ns);
   std::vector<double> gm1, gm2;
   run(2, g1, gm1);
+  run(3, g2, gm2);
   auto check = [&](const char* name, const float* g, const std::vector<double>& gm) {
     double num = 0, den = 0, worst = 0;
     for (size_t i = 0; i < ns; ++i) {
@@ -484,8 +486,9 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
     printf("%s %-58s %s  d/dsrc rel-L2 %.2e max-abs %.2e, d/dM rel-L2 %.2e\n", ok ? "ok  " : "FAIL", name, tag.c_str(), e_src, worst, e_m);
     if (!ok) ++failures;
   };
-  printf("     pixels on the exact (global-memory) path: warp_bwd_tma2 %lld of %d\n", exact[2], B * h * w);
+  printf("     pixels on the exact (global-memory) path: warp_bwd_tma2 %lld, stride-1 lanes %lld of %d\n", exact[2], exact[3], B * h * w);
   check("warp_bwd_tma2 (per-warp pipelines) vs fp64 scalar backward", g1, gm1);
+  check("warp_bwd_tma2<STRIDE1> (conflict-free lanes) vs fp64 scalar backward", g2, gm2);
 }
 
 // Random shapes, grids and completion modes (run_emu --fuzz N): shakes out the edge cases the fixed list does not name
