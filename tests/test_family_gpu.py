@@ -236,3 +236,66 @@ def test_fused_unsharp_equals_blur_then_lerp(ks, border):
     leaf = x.clone().requires_grad_(True)
     K.filters.unsharp_mask(leaf, (ks, ks), (1.3, 1.7), border).sum().backward()
     assert leaf.grad is not None
+
+
+def test_install_on_a_package_with_the_references_layout(tmp_path, monkeypatch):
+    """install() on the GPU box, where the reference itself cannot be imported: a throw-away package with Kornia's module layout
+    (defining modules, re-export sites, a caller that did ``from ..geometry.transform import warp_perspective`` and one that
+    captured the function at import) is rebound, its callers then run on the CUDA kernels, uninstall() restores it."""
+    import importlib
+    import sys
+    import textwrap
+
+    root = tmp_path / "fakekornia"
+    files = {
+        "__init__.py": "from . import geometry, filters, metrics, augmentation\n",
+        "geometry/__init__.py": "from .transform import *\n",
+        "geometry/transform/__init__.py": "from .imgwarp import *\n",
+        "geometry/transform/imgwarp.py": """
+            __all__ = ["warp_perspective", "warp_affine", "remap", "get_perspective_transform"]
+            def warp_perspective(*a, **k): raise AssertionError("the original warp_perspective ran")
+            def warp_affine(*a, **k): raise AssertionError("the original warp_affine ran")
+            def remap(*a, **k): raise AssertionError("the original remap ran")
+            def get_perspective_transform(*a, **k): raise AssertionError("the original get_perspective_transform ran")
+            """,
+        "filters/__init__.py": "from .filter import filter2d, filter2d_separable\nfrom .gaussian import gaussian_blur2d\nfrom .sobel import spatial_gradient, sobel\n",
+        "filters/filter.py": "def filter2d(*a, **k): raise AssertionError('original')\ndef filter2d_separable(*a, **k): raise AssertionError('original')\n",
+        "filters/gaussian.py": "def gaussian_blur2d(*a, **k): raise AssertionError('original')\n",
+        "filters/sobel.py": "def spatial_gradient(*a, **k): raise AssertionError('original')\ndef sobel(*a, **k): raise AssertionError('original')\n",
+        "metrics/__init__.py": "from .ssim import ssim\n",
+        "metrics/ssim.py": "def ssim(*a, **k): raise AssertionError('original')\n",
+        "augmentation/__init__.py": """
+            from ..geometry.transform import get_perspective_transform, warp_perspective
+            from ..filters import gaussian_blur2d
+            def random_perspective(x, src, dst):
+                return warp_perspective(x, get_perspective_transform(src, dst), tuple(x.shape[-2:]))
+            def blur(x):
+                return gaussian_blur2d(x, (5, 5), (1.0, 1.0))
+            """,
+    }
+    for rel, text in files.items():
+        path = root / rel
+        path.parent.mkdir(parents=True, exist_ok=True)
+        path.write_text(textwrap.dedent(text))
+    monkeypatch.syspath_prepend(str(tmp_path))
+    fake = importlib.import_module("fakekornia")
+    try:
+        x = torch.rand(4, 3, 64, 96, device=DEV)
+        quad = torch.tensor([[0.0, 0], [95, 0], [95, 63], [0, 63]], device=DEV)[None].repeat(4, 1, 1)
+        dst = quad + torch.randn(4, 4, 2, device=DEV)
+        with pytest.raises(AssertionError):
+            fake.augmentation.random_perspective(x, quad, dst)
+        K.install(fake)
+        before = K._ops.launch_count
+        out = fake.augmentation.random_perspective(x, quad, dst)
+        blurred = fake.augmentation.blur(x)
+        assert K._ops.launch_count >= before + 3 and out.shape == x.shape and blurred.shape == x.shape
+        assert torch.equal(out, K.warp_perspective(x, K.geometry.transform.get_perspective_transform(quad, dst), (64, 96)))
+        assert fake.geometry.warp_affine is K.warp_affine and fake.filters.filter2d is K.filter2d and fake.metrics.ssim is K.metrics.ssim
+        K.uninstall()
+        with pytest.raises(AssertionError):
+            fake.augmentation.blur(x)
+    finally:
+        K.uninstall()
+        for name in [n for n in sys.modules if n == "fakekornia" or n.startswith("fakekornia.")]:
+            del sys.modules[name]
