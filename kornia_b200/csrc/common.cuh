@@ -84,7 +84,7 @@ enum Option {
   OPT_SEP_VWALK,       // band-walking separable filter: -1 auto (11 taps and more), 0 never, 1 whenever it applies
   OPT_TILED_GRADIENT,  // shared-memory derivative stencils (off: gradient.cuh)
   OPT_U8_TILED,        // staged-window uint8 ingest warp (off: per-tap kernel)
-  OPT_BWD_STRIDE1,     // tiled backward on conflict-free stride-1 lanes (off: column-pair lanes)
+  OPT_BWD_STRIDE1,     // tiled backward on stride-1 lanes (default; 0: the column-pair lanes, 5 % slower at cfg4)
   OPT_COUNT
 };
 int option(Option o);

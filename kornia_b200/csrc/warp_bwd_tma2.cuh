@@ -19,8 +19,8 @@
 //   * no CTA-wide barrier or handshake inside the tile loop: 16 independent warps per SM hide each other's latency.
 // Shared memory: 8 x (window + strip) = 110.6 KB per CTA with both gradients -> still 2 CTAs/SM.
 //
-// Measured on B200 (round 2): bit-identical d/dsrc up to the order of the TMA reduce-adds; 1.68 ms at B=128x3x720x1280 with
-// both gradients (round 1's shared-stage kernel: 1.90 ms).
+// Measured on B200 (round 2): bit-identical d/dsrc up to the order of the TMA reduce-adds; at B=128x3x720x1280 with both gradients
+// 1.71 ms on column-pair lanes, 1.62 ms on stride-1 lanes (STRIDE1, the default; round 1's shared-stage kernel: 1.90 ms).
 #pragma once
 #include <type_traits>
 
