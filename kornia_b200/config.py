@@ -22,7 +22,7 @@ import os
 
 from . import _lib
 
-DEVICE_OPTIONS = ("tma", "tiled_filter", "square_tiles", "sep_vwalk", "tiled_gradient", "u8_tiled", "bwd_stride1")
+DEVICE_OPTIONS = ("tma", "tiled_filter", "square_tiles", "sep_vwalk", "tiled_gradient", "u8_tiled", "bwd_stride1", "remap_piped")
 _HOST_DEFAULTS = {"fused_pyrdown": 1, "fused_undistort": 1, "fast_filter_bwd": 1, "torch_prelude": 0}
 
 

@@ -85,6 +85,7 @@ enum Option {
   OPT_TILED_GRADIENT,  // shared-memory derivative stencils (off: gradient.cuh)
   OPT_U8_TILED,        // staged-window uint8 ingest warp (off: per-tap kernel)
   OPT_BWD_STRIDE1,     // tiled backward on stride-1 lanes (default; 0: the column-pair lanes, 5 % slower at cfg4)
+  OPT_REMAP_PIPED,     // remap on the pipelined persistent kernel (off: one CTA per tile)
   OPT_COUNT
 };
 int option(Option o);

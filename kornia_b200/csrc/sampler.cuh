@@ -48,22 +48,27 @@ __device__ __forceinline__ float interior_reflection(float c) {
   return c;
 }
 
-// reflect_coord + clip_coord ('reflection' of a bilinear / nearest coordinate, GridSampler.h:89-105,143-160) without fmod / div for
-// coordinates within one span of the image -- which is every pixel of a border tile: |c - lo| < span has flips = 0 and
-// fmod = identity, span <= |c - lo| < 2 span has flips = 1 and fmod(a, span) = a - span EXACTLY (Sterbenz), anything further
-// out takes reflect_coord itself.  Bit-identical to clip_coord(reflect_coord(...)) for every input (tools/hostemu checks it).
+// reflect_coord + clip_coord ('reflection' of a bilinear / nearest coordinate, GridSampler.h:89-105,143-160) as straight-line
+// code for coordinates within one span of the image -- which is every pixel of a border tile: |c - lo| < span has flips = 0 and
+// fmod = identity, span <= |c - lo| < 2 span has flips = 1 and fmod(a, span) = a - span EXACTLY (Sterbenz).  Anything further out
+// (or NaN) raises `far` and the caller sends the pixel to its exact path, where reflect_coord itself runs.  Bit-identical to
+// clip_coord(reflect_coord(...)) wherever `far` stays false (tools/hostemu checks it).
+// (Round 2, measured: with the general reflect_coord inlined as a third branch here, the 7 % border tiles of a 1080p warp cost
+//  3.5 x an interior tile and the pipelined remap ran at 34-48 % of its roofline -- profiles/r2_ab_remap_B64.txt.)
+template <typename T>
+__device__ __forceinline__ T reflect_clip_near_rt(T c, int size, bool align, bool& far) {
+  using R = RN<T>;
+  const int tl = align ? 0 : -1, th = align ? 2 * (size - 1) : 2 * size - 1;
+  if (tl == th) return T(0);  // a one-texel axis under align_corners (uniform)
+  const T lo = T(tl) * T(0.5), span = T(th - tl) * T(0.5);
+  const T a = R::abs(R::sub(c, lo));
+  far = far || !(a < T(2) * span);
+  const T e = a < span ? a : R::sub(span, R::sub(a, span));
+  return clip_coord(R::add(e, lo), size);
+}
 template <bool ALIGN>
-__device__ __forceinline__ float reflect_clip_fast(float c, int size) {
-  using R = RN<float>;
-  const int tl = ALIGN ? 0 : -1, th = ALIGN ? 2 * (size - 1) : 2 * size - 1;
-  if (tl == th) return 0.f;
-  const float lo = (float)tl * 0.5f, span = (float)(th - tl) * 0.5f;
-  const float a = R::abs(R::sub(c, lo));
-  float r;
-  if (a < span) r = R::add(a, lo);
-  else if (a < 2.f * span) r = R::add(R::sub(span, R::sub(a, span)), lo);
-  else r = reflect_coord(c, tl, th);
-  return clip_coord(r, size);
+__device__ __forceinline__ float reflect_clip_near(float c, int size, bool& far) {
+  return reflect_clip_near_rt<float>(c, size, ALIGN, far);
 }
 
 // values that cannot be an index (NaN, +-inf, beyond int range) become -100: out of bounds
@@ -77,8 +82,13 @@ __device__ __forceinline__ T pad_coord(T c, int size, bool align) {
   if (PAD == KB200_BORDER) {
     c = clip_coord(c, size);
   } else if (PAD == KB200_REFLECTION) {
-    c = align ? reflect_coord(c, 0, 2 * (size - 1)) : reflect_coord(c, -1, 2 * size - 1);
-    c = clip_coord(c, size);
+    // within one span of the image (all but pathological maps) the reflection is two subtractions and a select; only beyond that
+    // the general form with fmod / division runs.  Both agree bit for bit where the first applies.  (Measured, round 2: with the
+    // general form alone, the exact-path pixels of ONE badly fitting sample made its CTAs stragglers -- the 'reflection' warp took
+    // 765 us against 544 us for 'zeros' at B=64 with equal average SM time, profiles/r2_reflection_B64_straggler.txt.)
+    bool far = false;
+    const T near = reflect_clip_near_rt<T>(c, size, align, far);
+    c = far ? clip_coord(align ? reflect_coord(c, 0, 2 * (size - 1)) : reflect_coord(c, -1, 2 * size - 1), size) : near;
   }
   return guard_index(c);
 }

@@ -501,11 +501,14 @@ def test_tiled_filter2d_bit_identical_to_generic(k, border):
                 torch.testing.assert_close(a.cpu(), want, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("piped", [0, 1])
 @pytest.mark.parametrize("pad", ["zeros", "border", "reflection"])
 @pytest.mark.parametrize("ac", [None, True])
 @pytest.mark.parametrize("C", [3, 1])
-def test_tiled_remap_bit_identical_to_generic(pad, ac, C):
-    """Smooth maps (served from the staged box), a noisy map (mostly exact path), out-of-view and NaN entries."""
+def test_tiled_remap_bit_identical_to_generic(piped, pad, ac, C):
+    """Smooth maps (served from the staged box), a noisy map (mostly exact path), out-of-view and NaN entries; both tiled kernels
+    (one CTA per tile / the pipelined persistent kernel, switch remap_piped)."""
+    K.config.set("remap_piped", piped)
     H, W, h, w = 96, 160, 80, 136
     g = torch.Generator().manual_seed(4)
     img = torch.rand(3, C, H, W, generator=g).to(DEV)
@@ -526,6 +529,27 @@ def test_tiled_remap_bit_identical_to_generic(pad, ac, C):
     want = R.remap(img.cpu()[:1], smooth_x[None], smooth_y[None], padding_mode=pad, align_corners=ac)
     got = K.remap(img[:1], smooth_x[None].to(DEV), smooth_y[None].to(DEV), padding_mode=pad, align_corners=ac)
     torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("pad", ["zeros", "reflection"])
+def test_piped_remap_many_strips(pad):
+    """More strips than persistent CTAs (segments start inside strips, every buffer is reused many times), per-sample and shared
+    maps, normalised coordinates: the pipelined kernel against the one-CTA-per-tile kernel, bit for bit."""
+    B, H, W = 40, 200, 264   # 40 x 7 = 280 strips of 5 tiles
+    g = torch.Generator().manual_seed(11)
+    img = torch.rand(B, 3, H, W, generator=g).to(DEV)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    amp = torch.linspace(0.0, 6.0, B)[:, None, None]
+    mx = (xs[None] + amp * torch.sin(ys / 17.0)[None] - 2.0).contiguous().to(DEV)
+    my = (ys[None] + amp * torch.cos(xs / 23.0)[None] + 1.5).contiguous().to(DEV)
+    for (ax, ay, norm) in ((mx, my, False), (mx[:1], my[:1], False), (2 * mx / (W - 1) - 1, 2 * my / (H - 1) - 1, True)):
+        with K.config.override(remap_piped=0):
+            want = K.remap(img, ax, ay, padding_mode=pad, align_corners=True, normalized_coordinates=norm)
+        with K.config.override(remap_piped=1):
+            n0 = K._ops.launch_count
+            got = K.remap(img, ax, ay, padding_mode=pad, align_corners=True, normalized_coordinates=norm)
+            assert K._ops.launch_count - n0 == 1
+        assert torch.equal(got, want), float((got - want).abs().max())
 
 
 # ------------------------------------------------------------------ contract details on the device

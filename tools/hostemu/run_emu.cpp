@@ -14,7 +14,7 @@
 #include "../../kornia_b200/csrc/gradient_tiled.cuh"
 #include "../../kornia_b200/csrc/sepfilter_vwalk.cuh"
 #include "../../kornia_b200/csrc/ssim_vwalk.cuh"
-#include "../../kornia_b200/csrc/remap_tiled.cuh"
+#include "../../kornia_b200/csrc/remap_piped.cuh"
 #include "ref_ssim_tiled.cuh"
 #include "../../kornia_b200/csrc/warp_bwd_tma2.cuh"
 #include "../../kornia_b200/csrc/warp_u8_tiled.cuh"
@@ -30,6 +30,7 @@ alignas(128) unsigned char gradt_smem[256 * 1024];
 alignas(128) unsigned char ssimv_smem[256 * 1024];
 alignas(128) float ssim_smem[64 * 1024];
 alignas(128) unsigned char remap_smem[256 * 1024];
+alignas(128) unsigned char remap_piped_smem[256 * 1024];
 alignas(128) unsigned char tma_smem[256 * 1024];
 alignas(128) unsigned char bwd2_smem[256 * 1024];
 alignas(128) unsigned char u8t_smem[256 * 1024];
@@ -338,6 +339,57 @@ static void test_undistort(int B, int H, int W, bool lazy, bool strong = false) 
   }
 }
 
+
+// remap_piped_kernel (persistent, map tiles and boxes through TMA, producer-side bounding boxes) against remap_tiled_kernel on
+// the same maps: bit for bit.  kind 0: smooth displacement; 1: smooth + a few wild / non-finite entries (exact path, disabled
+// boxes); 2: strong shear (tiles that do not fit a box).
+template <int NC, int PAD, bool ALIGN>
+static void test_remap_piped(int B, int H, int W, int h, int w, unsigned grid, bool lazy, int kind, bool shared_map, bool normalized) {
+  emu::lazy_tma = lazy;
+  std::vector<float> ss, o1s, o2s, mxs, mys;
+  const size_t ns = (size_t)B * NC * H * W, no = (size_t)B * NC * h * w;
+  const int Bmap = shared_map ? 1 : B;
+  const size_t nm = (size_t)Bmap * h * w;
+  float* src = aligned(ss, ns);
+  for (size_t i = 0; i < ns; ++i) src[i] = randv(1)[0];
+  float* mx = aligned(mxs, nm);
+  float* my = aligned(mys, nm);
+  for (int b = 0; b < Bmap; ++b)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        const float u = (float)x / std::max(1, w - 1), v = (float)y / std::max(1, h - 1);
+        float a = u * (W - 1) + 3.5f * sinf(6.f * v + b) - 2.f + (kind == 2 ? 40.f * v : 0.f);
+        float c = v * (H - 1) + 2.5f * cosf(5.f * u + b) + 1.f;
+        if (kind == 1) {
+          const unsigned hsh = (unsigned)(x * 7919 + y * 104729 + b * 31) % 97u;
+          if (hsh == 0) a += 300.f;
+          if (hsh == 1) c = -1.0e9f;
+          if (hsh == 2 && (x % 64) == 5) a = NAN;
+          if (hsh == 3 && y == h / 2) c = INFINITY;
+        }
+        if (normalized) {
+          a = 2.f * a / std::max(1, W - 1) - 1.f;
+          c = 2.f * c / std::max(1, H - 1) - 1.f;
+        }
+        mx[((size_t)b * h + y) * w + x] = a;
+        my[((size_t)b * h + y) * w + x] = c;
+      }
+  const CUtensorMap map = emu::make_map(src, W, H, B * NC, 72, 40, NC);
+  const CUtensorMap mmx = emu::make_map(mx, w, h, Bmap, 64, 32, 1), mmy = emu::make_map(my, w, h, Bmap, 64, 32, 1);
+  const std::string tag = std::to_string(B) + "x" + std::to_string(NC) + "x" + std::to_string(H) + "x" + std::to_string(W) + " -> " + std::to_string(h) + "x" +
+                          std::to_string(w) + " pad=" + std::to_string(PAD) + (ALIGN ? " align" : "") + " grid=" + std::to_string(grid) + (lazy ? " lazy" : " eager") +
+                          " kind=" + std::to_string(kind) + (shared_map ? " shared" : "") + (normalized ? " normalized" : "");
+  float* o1 = aligned(o1s, no);
+  float* o2 = aligned(o2s, no);
+  for (size_t i = 0; i < no; ++i) o1[i] = o2[i] = -7.f;
+  RemapTiledParams p{src, mx, my, o1, B, H, W, h, w, Bmap, normalized ? 1 : 0, nullptr};
+  emu::set_smem(remap_smem, sizeof(remap_smem));
+  emu::launch3(dim3(ceil_div(w, 64), ceil_div(h, 32), B), dim3(256), [&] { remap_tiled_kernel<NC, PAD, ALIGN, false>(map, p); });
+  p.out = o2;
+  emu::set_smem(remap_piped_smem, sizeof(remap_piped_smem));
+  emu::launch(grid, dim3(TMA_THREADS), [&] { remap_piped_kernel<NC, PAD, ALIGN>(map, mmx, mmy, p); });
+  compare("remap_piped_kernel vs remap_tiled_kernel " + tag, o2, o1, no);
+}
 
 // ------------------------------------------------------------------------------------------ tiled warp forward (the headline kernel)
 template <bool PROJ, int PAD, int TW, int TH, int BW, int BH, int INTERP = KB200_BILINEAR, bool ALIGN = true>
@@ -656,13 +708,73 @@ static void test_u8_all() {
   test_u8_undistort<1>(1, 33, 64, 0, false);
 }
 
+
+// reflect_clip_near_rt (two subtractions and a select) against clip_coord(reflect_coord(...)) (fmod, division, floor): every float
+// within 300 ulps of a multiple of the span and a random sweep of +-3 spans, for several sizes and both align_corners settings.
+static void test_reflect_near() {
+  long long checked = 0, bad = 0, fars = 0;
+  std::mt19937 g(7);
+  for (int size : {1, 2, 3, 5, 64, 720, 1080, 1920, 4099})
+    for (int align = 0; align < 2; ++align) {
+      const int tl = align ? 0 : -1, th = align ? 2 * (size - 1) : 2 * size - 1;
+      const float lo = tl * 0.5f, span = (th - tl) * 0.5f;
+      auto check = [&](float c) {
+        bool far = false;
+        const float got = reflect_clip_near_rt<float>(c, size, align != 0, far);
+        const float want = clip_coord(reflect_coord(c, tl, th), size);
+        ++checked;
+        if (far) { ++fars; return; }
+        if (memcmp(&got, &want, 4) != 0 && !(got == 0.f && want == 0.f)) {
+          if (bad < 5) printf("     reflect mismatch size=%d align=%d c=%.9g got %.9g want %.9g\n", size, align, c, got, want);
+          ++bad;
+        }
+      };
+      for (int k = -3; k <= 3; ++k) {
+        float c = lo + k * span;
+        for (int i = 0; i < 300; ++i) c = nextafterf(c, -INFINITY);
+        for (int i = 0; i < 600; ++i, c = nextafterf(c, INFINITY)) check(c);
+      }
+      for (int i = 0; i < 20000; ++i) check(lo + ((float)(g() % 2000001) / 1000000.f - 1.f) * 3.f * std::max(span, 1.f));
+      check(NAN); check(INFINITY); check(-INFINITY); check(1e30f);
+    }
+  printf("%s reflect_clip_near_rt == clip_coord(reflect_coord) on %lld coordinates (%lld beyond two spans left to the general form)\n", bad ? "FAIL" : "ok  ",
+         checked, fars);
+  if (bad) ++failures;
+}
+
+// run_emu --probe PAD: one 540 x 960 sample under a bench-like homography (a few pixels of shift, 1 % scale): how many tiles run
+// the INNER copy and how many pixels leave the shared-memory path, per padding mode.
+template <int PAD>
+static void probe_forward() {
+  constexpr int C = 3, H = 540, W = 960;
+  emu::lazy_tma = false;
+  emu::set_smem(tma_smem, sizeof(tma_smem));
+  std::vector<float> ss, o1s;
+  float* src = aligned(ss, (size_t)C * H * W);
+  for (size_t i = 0; i < (size_t)C * H * W; ++i) src[i] = randv(1)[0];
+  std::vector<float> bx(W), by(H);
+  for (int i = 0; i < W; ++i) bx[i] = ((float)i / (float)(W - 1) - 0.5f) * 2.f;
+  for (int i = 0; i < H; ++i) by[i] = ((float)i / (float)(H - 1) - 0.5f) * 2.f;
+  const float M[9] = {1.0013f, 0.0006f, -4.24f * 2.f / (W - 1), 0.0015f, 1.0155f, -9.04f * 2.f / (H - 1), 0.001f, 0.0004f, 1.f};
+  float* o1 = aligned(o1s, (size_t)C * H * W);
+  TmaWarpParams p{};
+  const float fillc[3] = {0.25f, 0.5f, 0.75f};
+  p.src = src; p.m = M; p.bx = bx.data(); p.by = by.data(); p.fill = fillc; p.out = o1;
+  p.B = 1; p.H = H; p.W = W; p.h = H; p.w = W; p.Bm = 1; p.align = 1; p.only_class = 0;
+  const CUtensorMap map = emu::make_map(src, W, H, C, 72, 40, C);
+  emu_careful_pixels = emu_inner_tiles = emu_other_tiles = 0;
+  emu::launch(4, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, KB200_BILINEAR, PAD, true, true, 64, 32, 72, 40, 2>(map, p); });
+  printf("pad=%d: tiles INNER %lld other %lld (each counted once per CTA), pixels on the exact path %lld of %d\n", PAD, emu_inner_tiles, emu_other_tiles,
+         emu_careful_pixels, H * W);
+}
+
 static void fuzz(int rounds) {
   std::mt19937 g(20260923);
   auto pick = [&](int lo, int hi) { return lo + (int)(g() % (unsigned)(hi - lo + 1)); };
   for (int r = 0; r < rounds; ++r) {
     const int H = pick(1, 110), W = 4 * pick(1, 70), planes = pick(1, 4), lazy = pick(0, 1);
     const unsigned grid = (unsigned)pick(1, 9);
-    switch (pick(0, 30)) {
+    switch (pick(0, 34)) {
       case 25: if (H > 1) test_forward<true, KB200_REFLECTION, 64, 32, 72, 40, KB200_BILINEAR, false>(3, H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 1)); break;
       case 26: if (H > 1) test_forward<true, KB200_FILL, 64, 32, 72, 40, KB200_BILINEAR, false>(3, H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 1)); break;
       case 27: if (H > 1) test_forward<false, KB200_REFLECTION, 64, 32, 72, 40, KB200_NEAREST, true>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
@@ -673,6 +785,10 @@ static void fuzz(int rounds) {
       case 11: if (H > 3 && W > 3) test_filter2d<7, KB200_REPLICATE>(planes, H, W, grid, lazy); break;
       case 12: test_filter2d<7, KB200_CONSTANT>(planes, H, W, grid, lazy); break;
       case 13: if (H > 1) test_undistort(pick(1, 2), H, W, lazy); break;
+      case 31: test_remap_piped<3, KB200_ZEROS, true>(pick(1, 3), H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 2), pick(0, 1), pick(0, 1)); break;
+      case 32: test_remap_piped<3, KB200_BORDER, false>(pick(1, 3), H, W, pick(1, 80), 4 * pick(1, 40), grid, lazy, pick(0, 2), pick(0, 1), pick(0, 1)); break;
+      case 33: test_remap_piped<1, KB200_REFLECTION, false>(pick(1, 3), H, W, H, W, grid, lazy, pick(0, 2), pick(0, 1), pick(0, 1)); break;
+      case 34: test_remap_piped<3, KB200_REFLECTION, true>(pick(1, 2), H, W, std::max(1, H - pick(0, 5)), W, grid, lazy, pick(0, 2), pick(0, 1), pick(0, 1)); break;
       case 14: if (H > 1 && W > 4) test_backward<true>(3, H, W, std::max(2, H - pick(0, 3)), std::max(8, W - 4 * pick(0, 2)), grid, lazy, pick(0, 1)); break;
       case 16: if (H > 1) test_forward<true, KB200_ZEROS, 64, 32, 72, 40>(3, H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 1)); break;
       case 17: if (H > 1) test_forward<false, KB200_BORDER, 32, 32, 56, 56>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
@@ -699,8 +815,16 @@ static void fuzz(int rounds) {
 }
 
 int main(int argc, char** argv) {
+  if (argc == 2 && std::string(argv[1]) == "--probe") {
+    probe_forward<KB200_ZEROS>();
+    probe_forward<KB200_BORDER>();
+    probe_forward<KB200_REFLECTION>();
+    return 0;
+  }
   if (argc == 3 && std::string(argv[1]) == "--fuzz") {
     fuzz(atoi(argv[2]));
+    printf("tiles of the forward kernel served by the INNER ('reflection', inside the image) copy of the unit code: %lld of %lld\n", emu_inner_tiles,
+           emu_inner_tiles + emu_other_tiles);
     printf("%s: %d failing comparisons in the fuzz run\n", failures ? "FAILED" : "PASSED", failures);
     return failures ? 1 : 0;
   }
@@ -726,9 +850,15 @@ int main(int argc, char** argv) {
     test_ssim<3>(1, 32, 64, 1, lazy);
     test_ssim<7>(2, 97, 260, 7, lazy);
     test_ssim<9>(1, 6, 8, 1, lazy);
+    if (!lazy) test_reflect_near();
     test_undistort(2, 70, 132, lazy);
     test_undistort(1, 33, 64, lazy);
     test_undistort(2, 97, 200, lazy, true);
+    test_remap_piped<3, KB200_ZEROS, true>(2, 70, 132, 70, 132, 3, lazy, 0, false, false);
+    test_remap_piped<3, KB200_BORDER, false>(3, 64, 128, 50, 100, 2, lazy, 1, true, false);
+    test_remap_piped<1, KB200_REFLECTION, true>(2, 97, 200, 97, 200, 5, lazy, 1, false, true);
+    test_remap_piped<3, KB200_REFLECTION, false>(1, 40, 72, 66, 132, 4, lazy, 2, false, false);
+    test_remap_piped<3, KB200_ZEROS, false>(2, 33, 64, 33, 64, 9, lazy, 0, true, true);
     test_forward<true, KB200_ZEROS, 64, 32, 72, 40>(3, 96, 200, 96, 200, 3, lazy, true);
     test_forward<true, KB200_ZEROS, 64, 32, 72, 40>(3, 70, 132, 50, 100, 2, lazy, false);
     test_forward<false, KB200_BORDER, 64, 32, 72, 40>(3, 64, 128, 70, 132, 4, lazy, true);

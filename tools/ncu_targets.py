@@ -1,6 +1,6 @@
 """One workload per kernel for `ncu --set full -k regex:<kernel>` captures (B=16 x 3 x 1080 x 1920, three calls):
     ncu --set full --clock-control none --import-source on -k regex:remap_tiled -s 2 -c 1 -o out python tools/ncu_targets.py remap
-targets: remap | filter2d | ssim | grad | bicubic | reflection | fill | blur17 | ingest"""
+targets (optional: batch, homography seed): remap | remap_reflection | filter2d | ssim | grad | bicubic | reflection | fill | blur11 | blur17 | ingest"""
 import os
 import sys
 
@@ -11,10 +11,16 @@ import bench  # noqa: E402
 import kornia_b200 as K  # noqa: E402
 
 which = sys.argv[1]
-B = 16
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 x = torch.rand(B, 3, 1080, 1920, device="cuda")
-M = bench.make_homographies(B, 3).cuda()
-if which == "remap":
+M = bench.make_homographies(B, int(sys.argv[3]) if len(sys.argv) > 3 else 3).cuda()
+if which == "remap_reflection":
+    ys, xs = torch.meshgrid(torch.arange(1080, dtype=torch.float32, device="cuda"), torch.arange(1920, dtype=torch.float32, device="cuda"), indexing="ij")
+    amp = torch.linspace(0.5, 4.0, B, device="cuda")[:, None, None]
+    mx = (xs[None] + amp * torch.sin(ys / 40.0)[None]).contiguous()
+    my = (ys[None] + amp * torch.cos(xs / 55.0)[None]).contiguous()
+    f = lambda: K.remap(x, mx, my, padding_mode="reflection", align_corners=True)  # noqa: E731
+elif which == "remap":
     ys, xs = torch.meshgrid(torch.arange(1080, dtype=torch.float32, device="cuda"), torch.arange(1920, dtype=torch.float32, device="cuda"), indexing="ij")
     r2 = ((xs - 960) / 960) ** 2 + ((ys - 540) / 540) ** 2
     mx = (960 + (xs - 960) * (1 + 0.02 * r2))[None].expand(B, -1, -1).contiguous()
@@ -28,6 +34,8 @@ elif which == "ssim":
     f = lambda: K.metrics.ssim(x, y, 11)  # noqa: E731
 elif which == "grad":
     f = lambda: K.filters.spatial_gradient(x, "sobel", 1)  # noqa: E731
+elif which == "blur11":
+    f = lambda: K.gaussian_blur2d(x, (11, 11), (2.0, 2.0))  # noqa: E731
 elif which == "blur17":
     f = lambda: K.gaussian_blur2d(x, (17, 17), (3.0, 3.0))  # noqa: E731
 elif which == "ingest":

@@ -21,7 +21,7 @@ step "4 ncu launch list of bench.py (final build)"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_bench_steps3.csv" \
   python bench.py --steps 3 --warmup 1 --no-cpu-baseline --no-side-legs > "$OUT/ncu_launches.log" 2>&1
 step "5 ncu --set full of the headline kernel at the headline batch"
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:warp_fwd_tma -s 7 -c 1 -o "$OUT/prof_fwd_B256" \
+timeout 500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:warp_fwd_tma.*int.64.*int.32.*int.72" -s 2 -c 1 -o "$OUT/prof_fwd_B256" \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-side-legs > "$OUT/ncu_fwd.log" 2>&1; tail -2 "$OUT/ncu_fwd.log" | tee -a "$OUT/steps.log"
 step "6 memcheck"
 timeout 400 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py > "$OUT/memcheck.txt" 2>&1; tail -3 "$OUT/memcheck.txt" | tee -a "$OUT/steps.log"
