@@ -220,6 +220,14 @@ def _wild_matrices(H, W):
     return torch.tensor(mats, dtype=torch.float32)
 
 
+def _shift_matrices(W):
+    """Tiles wholly outside the image by 20-50 px ('reflection' folds them back as a whole: the box must follow the reflected corners)
+    and a shift of more than one span (reflected twice: the exact path)."""
+    return torch.tensor([[[0.96, -0.013, 13.1], [-0.016, 0.95, 32.0], [-1.5e-5, -1.1e-5, 1]],
+                         [[1, 0, -50.0], [0, 1, -27.0], [0, 0, 1]],
+                         [[1, 0, 1.6 * W], [0, 1, 0], [0, 0, 1]]], dtype=torch.float32)
+
+
 _TILED_CASES = ([("bilinear", pad, C) for pad in ("zeros", "border", "reflection") for C in (1, 3, 4)] +
                 [("bilinear", "fill", 3)] +
                 [(mode, pad, 3) for mode in ("nearest", "bicubic") for pad in ("zeros", "border", "reflection", "fill")] +
@@ -232,7 +240,7 @@ def test_tiled_kernel_bit_identical_to_generic(mode, pad, C, ac):
     """Every mode the tiled kernel serves must reproduce the generic kernel exactly (the staged tile is only a
     cache): rotations, zoom, strong perspective, a horizon inside the image, everything out of view."""
     H, W = 216, 384
-    M = torch.cat([_wild_matrices(H, W), _bench_homographies(6, H, W, 5, sigma=4.0)]).to(DEV)
+    M = torch.cat([_wild_matrices(H, W), _shift_matrices(W), _bench_homographies(6, H, W, 5, sigma=4.0)]).to(DEV)
     src = torch.rand(M.shape[0], C, H, W, device=DEV)
     fv = torch.tensor([0.2, 0.5, 0.8], device=DEV) if pad == "fill" else None
     from kornia_b200 import _lib
