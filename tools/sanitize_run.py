@@ -18,6 +18,19 @@ s = src.clone().requires_grad_(True)
 m = M.clone().requires_grad_(True)
 out = K.warp_perspective(s, m, (H, W))
 torch.autograd.grad(out.sum(), [s, m])
+for pad in ("zeros", "border", "reflection"):  # 'reflection': INNER and border tiles, a sample shifted out of the image by 30 rows
+    Ms = M.clone()
+    Ms[0, 1, 2] += 30.0
+    K.warp_perspective(src, Ms, (H, W), padding_mode=pad)
+    K.warp_perspective(src, Ms, (H, W), mode="nearest", padding_mode=pad, align_corners=False)
+# remap: the pipelined persistent kernel (zeros / border, maps through TMA), the one-CTA-per-tile kernel (reflection; odd width)
+ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+mx = (xs + 3.0 * torch.sin(ys / 9.0) - 4.0)[None].repeat(B, 1, 1).to(dev)
+my = (ys + 2.5 * torch.cos(xs / 11.0) + 1.0)[None].repeat(B, 1, 1).to(dev)
+for pad in ("zeros", "border", "reflection"):
+    K.remap(src, mx, my, padding_mode=pad, align_corners=True)
+    K.remap(src, mx[:1], my[:1], padding_mode=pad)
+    K.remap(src, mx[:, :90, :150].contiguous(), my[:, :90, :150].contiguous(), padding_mode=pad)   # w % 4 != 0: not TMA-addressable
 K.gaussian_blur2d(src, (11, 11), (2.0, 2.0))
 K.gaussian_blur2d(src, (5, 5), (1.0, 1.0), "replicate")
 # image derivatives: odd width (scalar path), aligned width (vector path), backward, fused magnitude, 5x5 stencils
