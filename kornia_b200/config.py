@@ -9,7 +9,9 @@ to run a kernel against the one it stands in for.
 Device-side (forwarded to the C library): ``tma`` (TMA-tiled warp / remap / backward kernels; off = generic per-pixel
 kernels), ``tiled_filter`` (shared-memory filter kernels; off = generic), ``square_tiles`` (second forward tile shape for
 rotated samples), ``sep_vwalk`` (band-walking separable filter: -1 auto = 11 taps and more, 0 never, 1 whenever it
-applies), ``tiled_gradient``, ``u8_tiled`` (staged-window uint8 ingest warp; off = per-tap kernel).
+applies), ``tiled_gradient``, ``u8_tiled`` (staged-window uint8 ingest warp; off = per-tap kernel), ``bwd_stride1`` (tiled
+backward on stride-1 lanes; off = column-pair lanes), ``remap_piped`` (pipelined persistent remap kernel for 'zeros' / 'border';
+off = one CTA per tile).
 Host-side: ``fused_pyrdown`` (5x5 blur + 2x decimation in one kernel), ``fused_undistort`` (lens model evaluated inside
 the sampling kernel), ``fast_filter_bwd`` (input gradient of the separable filter through the one-pass forward kernel),
 ``torch_prelude`` (the (B,3,3) matrix chain as the reference's torch op sequence instead of one launch; needed for double

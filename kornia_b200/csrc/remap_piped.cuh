@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) remap_piped_kernel(const __gri
   const size_t oplane = (size_t)p.h * p.w, splane = (size_t)H * W;
   // Coordinates of this thread's eight pixels of walk wk's tile, out of its map tile (which goes back to the producer at once),
   // and this warp's share of the tile's bounding box, published for the producer.
-  auto stage_coordinates = [&](const Walk& wk, float (&ux)[NU], float (&uy)[NU]) {
+  auto stage_coordinates = [&](const Walk& wk, float (&ux)[NU], float (&uy)[NU], unsigned& farmask) {
+    farmask = 0u;
     const int s = wk.n % NS;
     const int ty = wk.strip % tiles_y;
     const int x0 = wk.tx * TW + lane, y_base = ty * TH + warp * RPW;
@@ -214,7 +215,14 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) remap_piped_kernel(const __gri
         if (!far) {
           lo_x = fminf(lo_x, ix); hi_x = fmaxf(hi_x, ix);
           lo_y = fminf(lo_y, iy); hi_y = fmaxf(hi_y, iy);
+        } else {
+          farmask |= 1u << u;
         }
+        // The PADDED coordinate is what stays in registers: the clamp is idempotent, and so is the near reflection (its half-pixel
+        // round trip returns the value it produced: tools/hostemu test_reflect_near), so the exact path may pad it again.  Only a
+        // `far` pixel needs its raw coordinate, and reads its map entry again for it.
+        ux[u] = ix;
+        uy[u] = iy;
       }
     }
 #pragma unroll
@@ -240,14 +248,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) remap_piped_kernel(const __gri
   walk_next(nw);
   walk_next(nw);  // one tile ahead
   float ux[NU], uy[NU];
-  if (cw.live) stage_coordinates(cw, ux, uy);
+  unsigned farmask = 0u;
+  if (cw.live) stage_coordinates(cw, ux, uy, farmask);
   while (cw.live) {
     const int s = cw.n % NS;
     const int b = cw.strip / tiles_y, ty = cw.strip - b * tiles_y;
     const int x0 = cw.tx * TW + lane, y_base = ty * TH + warp * RPW;
     // ---- 1. the next tile's coordinates and bounding box: the producer turns them into a box load while this tile is blended
     float nux[NU], nuy[NU];
-    if (nw.live) stage_coordinates(nw, nux, nuy);
+    unsigned nfarmask = 0u;
+    if (nw.live) stage_coordinates(nw, nux, nuy, nfarmask);
     // ---- 2. this tile's box
     tma::mbar_wait(&box_full[s], (cw.n / NS) & 1);
     const StageInfo si = info[s];
@@ -262,16 +272,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) remap_piped_kernel(const __gri
         const int x = x0 + 32 * j, y = y_base + i;
         if (x >= p.w || y >= p.h) continue;
         const int u = i * NJ + j;
-        float ix = ux[u], iy = uy[u];
-        if (PRECLAMP) {
-          ix = fminf(Wm1, fmaxf(ix, 0.f));
-          iy = fminf(Hm1, fmaxf(iy, 0.f));
-        }
-        bool far = false;
-        if (REFLECT) {  // the window test and the taps below see the reflected, clipped coordinate
-          ix = reflect_clip_near<ALIGN>(ix, W, far);
-          iy = reflect_clip_near<ALIGN>(iy, H, far);
-        }
+        const float ix = ux[u], iy = uy[u];  // padded already (stage_coordinates)
+        const bool far = REFLECT && ((farmask >> u) & 1u) != 0u;
         float* o = obase + (size_t)y * p.w + x;
         if (!far && ix >= si.lo_x && ix < si.hi_x && iy >= si.lo_y && iy < si.hi_y) {
           const float tX = __fadd_rd(ix, FLOOR_MAGIC), tY = __fadd_rd(iy, FLOOR_MAGIC);
@@ -289,8 +291,19 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) remap_piped_kernel(const __gri
             __stcs(o + c * oplane, a);
           }
         } else {
+          float ex = ix, ey = iy;
+          if (far) {  // beyond two spans: the raw coordinate, from the map entry (an L2 hit)
+            const size_t at = (p.Bmap == 1 ? 0 : (size_t)b * oplane) + (size_t)y * p.w + x;
+            float a = __ldg(p.map_x + at), c = __ldg(p.map_y + at);
+            if (!normalized) {
+              a = R::sub(R::mul(fx, a), 1.f);
+              c = R::sub(R::mul(fy, c), 1.f);
+            }
+            ex = unnorm<ALIGN>(a, Wm1, Wf);
+            ey = unnorm<ALIGN>(c, Hm1, Hf);
+          }
           PixelSampler<float, KB200_BILINEAR, PAD> S;
-          S.prepare(ux[u], uy[u], H, W, ALIGN);
+          S.prepare(ex, ey, H, W, ALIGN);
 #pragma unroll
           for (int c = 0; c < NC; ++c) __stcs(o + c * oplane, S.sample(sp + c * splane));
         }
@@ -303,6 +316,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) remap_piped_kernel(const __gri
       ux[u] = nux[u];
       uy[u] = nuy[u];
     }
+    farmask = nfarmask;
     walk_next(cw);
     walk_next(nw);
   }

@@ -41,8 +41,8 @@ static int launch_remap_piped(const CUtensorMap& msrc, const CUtensorMap& mmx, c
 int remap_piped_forward(const float* src, const float* map_x, const float* map_y, float* out, int B, int C, int H, int W, int h, int w,
                         int Bmap, int normalized, int pad, int align, cudaStream_t st) {
   if (!option(OPT_REMAP_PIPED)) return KB200_EUNSUPPORTED;
-  // measured (profiles/r2_ab_remap_B64.txt): the reflected coordinate costs this kernel 50 % more instructions (it is formed for the
-  // bounding box and again for the taps) and it ends 0.66-0.85x the one-CTA-per-tile kernel, which keeps 'reflection'
+  // measured (profiles/r2_ab_remap_B64.txt, three variants): under 'reflection' this kernel ends between 0.66x and 1.09x the
+  // one-CTA-per-tile kernel, which therefore keeps that mode
   if (pad == KB200_REFLECTION) return KB200_EUNSUPPORTED;
   if ((w % 4) != 0 || ((reinterpret_cast<uintptr_t>(map_x) | reinterpret_cast<uintptr_t>(map_y)) & 15) != 0) return KB200_EUNSUPPORTED;
   if ((long long)B * ceil_div(h, 32) > 0x7fffffffll || (long long)B * C > 0x7fffffffll) return KB200_EUNSUPPORTED;

@@ -724,6 +724,12 @@ static void test_reflect_near() {
         const float want = clip_coord(reflect_coord(c, tl, th), size);
         ++checked;
         if (far) { ++fars; return; }
+        bool far2 = false;  // idempotent: padding the padded coordinate again returns it (the pipelined remap relies on it)
+        const float again = reflect_clip_near_rt<float>(got, size, align != 0, far2);
+        if (far2 || (memcmp(&again, &got, 4) != 0 && !(again == 0.f && got == 0.f))) {
+          if (bad < 5) printf("     reflect not idempotent size=%d align=%d c=%.9g first %.9g second %.9g\n", size, align, c, got, again);
+          ++bad;
+        }
         if (memcmp(&got, &want, 4) != 0 && !(got == 0.f && want == 0.f)) {
           if (bad < 5) printf("     reflect mismatch size=%d align=%d c=%.9g got %.9g want %.9g\n", size, align, c, got, want);
           ++bad;

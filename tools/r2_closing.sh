@@ -29,4 +29,6 @@ step "7 tables at B=64"
 timeout 300 python tools/bench_modes.py > "$OUT/modes_B64.txt" 2>&1; cp gpurun_out/modes.json "$OUT/modes_B64.json" 2>/dev/null
 timeout 300 python tools/bench_filters.py > "$OUT/filters_remap_B64.txt" 2>&1
 timeout 300 python tools/bench_family.py > "$OUT/family_B64.txt" 2>&1
+timeout 300 python tools/ab_remap.py 64 > "$OUT/ab_remap_B64.txt" 2>&1
+timeout 300 python tools/diag_reflection.py > "$OUT/reflection_per_sample.txt" 2>&1
 ls -la "$OUT" | tee -a "$OUT/steps.log"
