@@ -43,7 +43,7 @@ int remap_piped_forward(const float* src, const float* map_x, const float* map_y
   if (!option(OPT_REMAP_PIPED)) return KB200_EUNSUPPORTED;
   // measured (profiles/r2_ab_remap_B64.txt, three variants): under 'reflection' this kernel ends between 0.66x and 1.09x the
   // one-CTA-per-tile kernel, which therefore keeps that mode
-  if (pad == KB200_REFLECTION) return KB200_EUNSUPPORTED;
+  if (pad == KB200_REFLECTION && option(OPT_REMAP_PIPED) < 2) return KB200_EUNSUPPORTED;  // remap_piped = 2: measure it anyway
   if ((w % 4) != 0 || ((reinterpret_cast<uintptr_t>(map_x) | reinterpret_cast<uintptr_t>(map_y)) & 15) != 0) return KB200_EUNSUPPORTED;
   if ((long long)B * ceil_div(h, 32) > 0x7fffffffll || (long long)B * C > 0x7fffffffll) return KB200_EUNSUPPORTED;
   EncodeTiledFn encode = encode_tiled_fn();
@@ -74,8 +74,10 @@ int remap_piped_forward(const float* src, const float* map_x, const float* map_y
     return align ? launch_remap_piped<NC_, PAD_, true>(msrc, mmx, mmy, p, st) : launch_remap_piped<NC_, PAD_, false>(msrc, mmx, mmy, p, st);
   KB_REMAP_CASE(3, KB200_ZEROS)
   KB_REMAP_CASE(3, KB200_BORDER)
+  KB_REMAP_CASE(3, KB200_REFLECTION)
   KB_REMAP_CASE(1, KB200_ZEROS)
   KB_REMAP_CASE(1, KB200_BORDER)
+  KB_REMAP_CASE(1, KB200_REFLECTION)
 #undef KB_REMAP_CASE
   return KB200_EUNSUPPORTED;
 }

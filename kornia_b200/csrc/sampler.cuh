@@ -58,9 +58,17 @@ __device__ __forceinline__ float interior_reflection(float c) {
 template <typename T>
 __device__ __forceinline__ T reflect_clip_near_rt(T c, int size, bool align, bool& far) {
   using R = RN<T>;
-  const int tl = align ? 0 : -1, th = align ? 2 * (size - 1) : 2 * size - 1;
-  if (tl == th) return T(0);  // a one-texel axis under align_corners (uniform)
-  const T lo = T(tl) * T(0.5), span = T(th - tl) * T(0.5);
+  if (align) {
+    // lo = 0, span = size - 1: c - 0 and e + 0 are the identity (e >= +0) and the reflected value already lies in [0, size - 1],
+    // so the clip is one too -- the general form below minus its four no-ops (16 -> 7 instructions per coordinate, which is what
+    // the 'reflection' remap was paying 32 times per pixel quad: profiles/r2_remap_piped_reflection_ncu_digest.txt)
+    if (size == 1) return T(0);  // a one-texel axis (uniform)
+    const T span = T(size - 1);
+    const T a = R::abs(c);
+    far = far || !(a < T(2) * span);
+    return a < span ? a : R::sub(span, R::sub(a, span));
+  }
+  const T lo = T(-0.5), span = T(size);
   const T a = R::abs(R::sub(c, lo));
   far = far || !(a < T(2) * span);
   const T e = a < span ? a : R::sub(span, R::sub(a, span));

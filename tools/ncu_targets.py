@@ -14,12 +14,12 @@ which = sys.argv[1]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 x = torch.rand(B, 3, 1080, 1920, device="cuda")
 M = bench.make_homographies(B, int(sys.argv[3]) if len(sys.argv) > 3 else 3).cuda()
-if which == "remap_reflection":
+if which in ("remap_reflection", "remap_border"):
     ys, xs = torch.meshgrid(torch.arange(1080, dtype=torch.float32, device="cuda"), torch.arange(1920, dtype=torch.float32, device="cuda"), indexing="ij")
     amp = torch.linspace(0.5, 4.0, B, device="cuda")[:, None, None]
     mx = (xs[None] + amp * torch.sin(ys / 40.0)[None]).contiguous()
     my = (ys[None] + amp * torch.cos(xs / 55.0)[None]).contiguous()
-    f = lambda: K.remap(x, mx, my, padding_mode="reflection", align_corners=True)  # noqa: E731
+    f = lambda: K.remap(x, mx, my, padding_mode=which[6:], align_corners=True)  # noqa: E731
 elif which == "remap":
     ys, xs = torch.meshgrid(torch.arange(1080, dtype=torch.float32, device="cuda"), torch.arange(1920, dtype=torch.float32, device="cuda"), indexing="ij")
     r2 = ((xs - 960) / 960) ** 2 + ((ys - 540) / 540) ** 2
