@@ -750,7 +750,7 @@ static void test_reflect_near() {
 
 // run_emu --probe PAD: one 540 x 960 sample under a bench-like homography (a few pixels of shift, 1 % scale): how many tiles run
 // the INNER copy and how many pixels leave the shared-memory path, per padding mode.
-template <int PAD>
+template <int PAD, int INTERP = KB200_BILINEAR>
 static void probe_forward() {
   constexpr int C = 3, H = 540, W = 960;
   emu::lazy_tma = false;
@@ -769,8 +769,8 @@ static void probe_forward() {
   p.B = 1; p.H = H; p.W = W; p.h = H; p.w = W; p.Bm = 1; p.align = 1; p.only_class = 0;
   const CUtensorMap map = emu::make_map(src, W, H, C, 72, 40, C);
   emu_careful_pixels = emu_inner_tiles = emu_other_tiles = 0;
-  emu::launch(4, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, KB200_BILINEAR, PAD, true, true, 64, 32, 72, 40, 2>(map, p); });
-  printf("pad=%d: tiles INNER %lld other %lld (each counted once per CTA), pixels on the exact path %lld of %d\n", PAD, emu_inner_tiles, emu_other_tiles,
+  emu::launch(4, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, INTERP, PAD, true, true, 64, 32, 72, 40, 2>(map, p); });
+  printf("interp=%d pad=%d: tiles INNER %lld other %lld (each counted once per CTA), pixels on the exact path %lld of %d\n", INTERP, PAD, emu_inner_tiles, emu_other_tiles,
          emu_careful_pixels, H * W);
 }
 
@@ -780,7 +780,13 @@ static void fuzz(int rounds) {
   for (int r = 0; r < rounds; ++r) {
     const int H = pick(1, 110), W = 4 * pick(1, 70), planes = pick(1, 4), lazy = pick(0, 1);
     const unsigned grid = (unsigned)pick(1, 9);
-    switch (pick(0, 34)) {
+    switch (pick(0, 40)) {
+      case 35: if (H > 1) test_forward<true, KB200_BORDER, 64, 32, 72, 40, KB200_BICUBIC, false>(3, H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 1)); break;
+      case 36: if (H > 1) test_forward<true, KB200_REFLECTION, 64, 32, 72, 40, KB200_BICUBIC, true>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
+      case 37: if (H > 1) test_forward<false, KB200_REFLECTION, 64, 32, 72, 40, KB200_BICUBIC, false>(3, H, W, std::max(1, H - pick(0, 5)), W, grid, lazy, pick(0, 1)); break;
+      case 38: if (H > 1) test_forward<true, KB200_FILL, 64, 32, 72, 40, KB200_BICUBIC, true>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
+      case 39: if (H > 1) test_forward<false, KB200_FILL, 32, 32, 56, 56, KB200_BICUBIC, false>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
+      case 40: if (H > 1) test_forward<true, KB200_BORDER, 32, 32, 56, 56, KB200_BICUBIC, true>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
       case 25: if (H > 1) test_forward<true, KB200_REFLECTION, 64, 32, 72, 40, KB200_BILINEAR, false>(3, H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 1)); break;
       case 26: if (H > 1) test_forward<true, KB200_FILL, 64, 32, 72, 40, KB200_BILINEAR, false>(3, H, W, std::max(1, H - pick(0, 5)), std::max(4, W - 4 * pick(0, 3)), grid, lazy, pick(0, 1)); break;
       case 27: if (H > 1) test_forward<false, KB200_REFLECTION, 64, 32, 72, 40, KB200_NEAREST, true>(3, H, W, H, W, grid, lazy, pick(0, 1)); break;
@@ -825,6 +831,10 @@ int main(int argc, char** argv) {
     probe_forward<KB200_ZEROS>();
     probe_forward<KB200_BORDER>();
     probe_forward<KB200_REFLECTION>();
+    probe_forward<KB200_ZEROS, KB200_BICUBIC>();
+    probe_forward<KB200_BORDER, KB200_BICUBIC>();
+    probe_forward<KB200_REFLECTION, KB200_BICUBIC>();
+    probe_forward<KB200_FILL, KB200_BICUBIC>();
     return 0;
   }
   if (argc == 3 && std::string(argv[1]) == "--fuzz") {
