@@ -86,6 +86,7 @@ enum Option {
   OPT_U8_TILED,        // staged-window uint8 ingest warp (off: per-tap kernel)
   OPT_BWD_STRIDE1,     // tiled backward on stride-1 lanes (default; 0: the column-pair lanes, 5 % slower at cfg4)
   OPT_REMAP_PIPED,     // remap on the pipelined persistent kernel (off: one CTA per tile)
+  OPT_DYN_SCHED,       // headline warp: strips handed out at run time in chunks (off: dealt out in advance)
   OPT_COUNT
 };
 int option(Option o);

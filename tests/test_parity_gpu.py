@@ -263,6 +263,32 @@ def test_tiled_kernel_bit_identical_to_generic(mode, pad, C, ac):
         assert same(a, b), ("affine", dsize, float((a - b).abs().nan_to_num().max()))
 
 
+def test_run_time_work_distribution_is_bit_identical():
+    """warp_fwd_tma<DYN> (strips handed out at run time in chunks, switch dyn_sched) against the static deal at a batch large enough
+    for the dispatcher to take it (B x ceil(h / 32) >= 8 x the SM count): the same tiles, the same results."""
+    B, H, W = 40, 1080, 1920
+    src = torch.rand(B, 3, H, W, device=DEV)
+    M = torch.cat([_bench_homographies(B - 4, H, W, 3), _wild_matrices(H, W)[:4]]).to(DEV)
+    fv = torch.tensor([0.2, 0.5, 0.8], device=DEV)
+    for fn in (lambda: K.warp_perspective(src, M, (H, W)), lambda: K.warp_affine(src, M[:, :2].contiguous(), (H, W), align_corners=False),
+               lambda: K.warp_perspective(src, M, (H, W), padding_mode="reflection"), lambda: K.warp_perspective(src, M, (H, W), padding_mode="border", align_corners=False),
+               lambda: K.warp_affine(src, M[:, :2].contiguous(), (H, W), padding_mode="fill", fill_value=fv)):
+        with K.config.override(dyn_sched=0):
+            want = fn()
+        with K.config.override(dyn_sched=1):
+            got = fn()
+        assert torch.equal(got, want), float((got - want).abs().max())
+    # ... and inside a CUDA graph: the launch allocates its work counter in stream order (cudaMallocAsync), which a capture records
+    many = torch.rand(400, 3, 96, 192, device=DEV)   # 1 200 strips of three tiles
+    Mm = _bench_homographies(400, 96, 192, 5).to(DEV)
+    with K.config.override(dyn_sched=0):
+        want = K.warp_perspective(many, Mm, (96, 192))
+    graphed = K.graphs.GraphedCall(lambda a, b: K.warp_perspective(a, b, (96, 192)), many, Mm)
+    for _ in range(3):
+        got = graphed(many, Mm)
+    assert torch.equal(got, want)
+
+
 def test_fast_division_is_ieee():
     """The shared-reciprocal division of the tiled kernel vs div.rn on 2^26 operand pairs in the ranges the
     normalised coordinates live in, plus wide-exponent pairs."""

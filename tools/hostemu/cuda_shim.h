@@ -109,5 +109,14 @@ inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) {
   memcpy(&v, &bits, sizeof(T));
   return v;
 }
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src, int = 32) {
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  bits = emu_warp_exchange(bits, src);
+  memcpy(&v, &bits, sizeof(T));
+  return v;
+}
+int atomicAdd(int*, int);
 float atomicAdd(float*, float);
 double atomicAdd(double*, double);

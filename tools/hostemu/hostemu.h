@@ -120,6 +120,7 @@ static void run_cta(dim3 block, const std::function<void()>& fn) {
   }
   for (;;) {
     unsigned live = 0, parked = 0, stuck = 0;
+    bool finished = false;  // a thread that ran to its end in this pass may have arrived on a barrier others spin on
     for (unsigned i = 0; i < n; ++i) {
       Fiber& f = fibers[i];
       if (f.done) continue;
@@ -132,7 +133,10 @@ static void run_cta(dim3 block, const std::function<void()>& fn) {
       threadIdx = f.tid;
       f.spinning = false;
       swapcontext(&sched_ctx, &f.ctx);
-      if (f.done) continue;
+      if (f.done) {
+        finished = true;
+        continue;
+      }
       if (f.at_barrier) ++parked;  // arrived during this pass
       else if (f.spinning) ++stuck;
     }
@@ -163,7 +167,7 @@ static void run_cta(dim3 block, const std::function<void()>& fn) {
       else if (fibers[i].spinning) ++spinning;
     }
     if (live == 0) break;
-    if (released) continue;
+    if (released || finished) continue;
     if (parked == live) {  // barrier complete
       for (unsigned i = 0; i < n; ++i) fibers[i].at_barrier = false;
       ++n_barriers;
@@ -257,6 +261,11 @@ float __fadd_rd(float a, float b) {
   volatile float r = va + vb;
   fesetround(old);
   return r;
+}
+int atomicAdd(int* p, int v) {
+  const int old = *p;
+  *p = old + v;
+  return old;
 }
 float atomicAdd(float* p, float v) {
   const float old = *p;

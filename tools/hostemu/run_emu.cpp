@@ -428,6 +428,21 @@ static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool 
   p.out = o1;
   const CUtensorMap map = emu::make_map(src, W, H, B * C, BW, BH, C);
   emu::launch(grid, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, INTERP, PAD, PROJ, ALIGN, TW, TH, BW, BH, 2>(map, p); });
+  if (INTERP == KB200_BILINEAR && TW == 64) {  // the run-time work distribution: same tiles, same results
+    std::vector<float> o3s;
+    float* o3 = aligned(o3s, no);
+    for (int chunk : {1, 3, 10}) {
+      for (size_t i = 0; i < no; ++i) o3[i] = -5.f;
+      int counter = 0;
+      TmaWarpParams q = p;
+      q.out = o3; q.counter = &counter; q.chunk_tiles = chunk;
+      emu::launch(grid, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, INTERP, PAD, PROJ, ALIGN, TW, TH, BW, BH, 2, true>(map, q); });
+      p.out = o3;  // keep the comparison below on o1
+      p.out = o1;
+      compare("warp_fwd_tma<DYN> chunk=" + std::to_string(chunk) + " vs the static deal " + std::to_string(B) + "x3x" + std::to_string(H) + "x" + std::to_string(W) +
+                  " grid=" + std::to_string(grid) + (lazy ? " lazy" : " eager"), o3, o2, no);
+    }
+  }
   compare(std::string("warp_fwd_tma (headline, verified on hw) vs its exact path ") + (PROJ ? "projective " : "affine ") + "interp=" + std::to_string(INTERP) + " pad=" + std::to_string(PAD) + " tile " +
               std::to_string(TW) + "x" + std::to_string(TH) + " " + std::to_string(B) + "x3x" + std::to_string(H) + "x" + std::to_string(W) + " -> " + std::to_string(h) +
               "x" + std::to_string(w) + " grid=" + std::to_string(grid) + (lazy ? " lazy" : " eager") + (tame ? " tame" : " wild") + (ALIGN ? "" : " align_corners=False"),

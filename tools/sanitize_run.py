@@ -14,6 +14,12 @@ M = M.to(dev)
 for mode in ("bilinear", "nearest", "bicubic"):
     for pad in ("zeros", "fill"):
         K.warp_perspective(src, M, (90, 200), mode=mode, padding_mode=pad, fill_value=torch.tensor([0.1, 0.2, 0.3], device=dev))
+# many strips (400 x 3 >= 8 x the SM count): the run-time work distribution of the headline kernel (warp_fwd_tma<DYN>)
+many = torch.rand(400, 3, 96, 192, generator=g).to(dev)
+Mmany = M[:1].expand(400, -1, -1).contiguous()
+K.warp_perspective(many, Mmany, (96, 192))
+K.warp_affine(many, Mmany[:, :2].contiguous(), (96, 192), align_corners=False)
+del many
 s = src.clone().requires_grad_(True)
 m = M.clone().requires_grad_(True)
 out = K.warp_perspective(s, m, (H, W))
