@@ -225,7 +225,7 @@ int kb200_warp_forward(const void* src, const void* m, const void* bx, const voi
 size_t kb200_warp_backward_workspace_bytes(int B, int h, int w, int dtype) {
   const size_t nblk = (size_t)ceil_div(w, GEN_BX) * ceil_div(h, GEN_BY);
   const size_t generic = (size_t)B * nblk * 9 * (dtype == KB200_F64 ? 8 : 4);
-  const size_t tiled = dtype == KB200_F32 ? bwd_tma_workspace_bytes(B, h) : 0;
+  const size_t tiled = dtype == KB200_F32 ? bwd_tma_workspace_bytes(B, h, w) : 0;
   return generic > tiled ? generic : tiled;
 }
 

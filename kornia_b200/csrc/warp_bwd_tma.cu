@@ -40,7 +40,11 @@ int warp_tma_backward(const float* gout, const float* src, const float* m, const
   p.gout = gout; p.src = src; p.m = m; p.bx = bx; p.by = by; p.gsrc = gsrc;
   p.B = B; p.H = H; p.W = W; p.h = h; p.w = w; p.Bm = Bm;
   p.max_segs = bwd_tma_max_segs(B, h);
-  const size_t rows = (size_t)bwd_tma_grid(B, h) * p.max_segs;
+  size_t rows = (size_t)bwd_tma_grid(B, h) * p.max_segs;
+  // run-time work distribution (warp_bwd_tma2<DYN>): RGB, stride-1 lanes, enough strips to go round several times
+  const bool dyn = C == 3 && option(OPT_DYN_SCHED) && option(OPT_BWD_STRIDE1) && (long long)B * ceil_div(h, 32) >= 4ll * bwd_tma_grid(B, h) &&
+                   bwd_tma_dyn_chunks(B, h, w) * TMA_CONSUMER_WARPS < 0x7fffffffll;
+  if (dyn) rows = (size_t)bwd_tma_dyn_chunks(B, h, w);  // one record row per chunk, all of them written
   if (gm) {
     p.records = reinterpret_cast<float*>(workspace);
     p.record_batch = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + rows * TMA_CONSUMER_WARPS * 9 * sizeof(float));
@@ -52,9 +56,19 @@ int warp_tma_backward(const float* gout, const float* src, const float* m, const
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return KB200_EUNSUPPORTED;
   }
-  const int rc = launch_warp_bwd_tma2(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, st);
+  if (dyn) {  // the launch's own work counter, allocated and released in stream order
+    if (cudaMallocAsync(reinterpret_cast<void**>(&p.counter), sizeof(int), st) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return KB200_EUNSUPPORTED;
+    }
+    cudaMemsetAsync(p.counter, 0, sizeof(int), st);
+    p.chunk_tiles = BWD_DYN_CHUNK;
+  }
+  const int rc = launch_warp_bwd_tma2(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, dyn, st);
+  if (dyn) cudaFreeAsync(p.counter, st);
   if (rc != KB200_OK || !gm) return rc;
-  warp_gm_reduce_records<<<dim3(9, Bm), 256, 0, st>>>(p.records, p.record_batch, gm, (int)rows, Bm);
+  warp_gm_reduce_records<<<dim3(9, Bm), 256, 0, st>>>(p.records, p.record_batch, gm, (int)rows, Bm,
+                                                        dyn ? (int)(rows / (size_t)B) : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("warp_gm_reduce_records launch failed: %s", cudaGetErrorString(e));

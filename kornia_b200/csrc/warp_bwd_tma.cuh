@@ -30,6 +30,8 @@ struct TmaBwdParams {
   float* records;      // (grid, max_segs, 8 warps, 9) partial sums for d/dm, or null
   int* record_batch;   // (grid, max_segs) batch index of each record row, -1 = unused
   int B, H, W, h, w, Bm, max_segs;
+  int* counter;        // DYN kernels only: zero-initialised work counter of this launch
+  int chunk_tiles;     // DYN kernels only: tiles per chunk
 };
 
 constexpr int BWD_SH = 8;         // rows of a warp's accumulation strip
@@ -81,11 +83,14 @@ __device__ __noinline__ float2 bwd_pixel_global(const TmaBwdParams& p, int b, in
 
 // Second stage of d/dm for the tiled kernel: fixed-order sum over the record rows of each sample.
 // grid = (9, Bm).  records (rows, 8, 9), record_batch (rows).
+// rows_per_batch > 0 (the run-time work distribution: row = chunk, the chunks of a sample are consecutive): only that sample's rows.
 static __global__ void __launch_bounds__(256) warp_gm_reduce_records(const float* __restrict__ records, const int* __restrict__ record_batch,
-                                                              float* __restrict__ gm, int rows, int Bm) {
+                                                              float* __restrict__ gm, int rows, int Bm, int rows_per_batch) {
   const int k = blockIdx.x, bm = blockIdx.y;
   double s = 0.0;
-  for (int r = threadIdx.x; r < rows; r += 256) {
+  const int r0 = (rows_per_batch > 0 && Bm != 1) ? bm * rows_per_batch : 0;
+  const int r1 = (rows_per_batch > 0 && Bm != 1) ? r0 + rows_per_batch : rows;
+  for (int r = r0 + threadIdx.x; r < r1; r += 256) {
     const int rb = record_batch[r];
     if (rb < 0 || (Bm != 1 && rb != bm)) continue;
     const float* rec = records + (size_t)r * TMA_CONSUMER_WARPS * 9 + k;
@@ -112,14 +117,17 @@ inline int bwd_tma_max_segs(int B, int h) {
   const long long nstrips = (long long)B * ceil_div(h, 32);
   return (int)(nstrips / bwd_tma_grid(B, h)) + 2;
 }
-inline size_t bwd_tma_workspace_bytes(int B, int h) {
-  const size_t rows = (size_t)bwd_tma_grid(B, h) * bwd_tma_max_segs(B, h);
+constexpr int BWD_DYN_CHUNK = 10;  // tiles per chunk of the run-time work distribution (warp_bwd_tma2<DYN>)
+inline long long bwd_tma_dyn_chunks(int B, int h, int w) { return (long long)B * ceil_div(h, 32) * ceil_div(ceil_div(w, 64), BWD_DYN_CHUNK); }
+inline size_t bwd_tma_workspace_bytes(int B, int h, int w) {  // record rows: one per (CTA, segment) of the static deal or one per chunk
+  size_t rows = (size_t)bwd_tma_grid(B, h) * bwd_tma_max_segs(B, h);
+  if ((size_t)bwd_tma_dyn_chunks(B, h, w) > rows) rows = (size_t)bwd_tma_dyn_chunks(B, h, w);
   return rows * (TMA_CONSUMER_WARPS * 9 * sizeof(float)) + rows * sizeof(int) + 256;
 }
 
 // msrcwin: tensor map of `src` with the per-warp window box (72, BWD_SH, C).
 int launch_warp_bwd_tma2(const CUtensorMap& msrcwin, const CUtensorMap& mgsrc, const CUtensorMap& mgout, const TmaBwdParams& p, int C, int pad,
-                         int projective, int align, bool need_src, bool need_m, cudaStream_t st);
+                         int projective, int align, bool need_src, bool need_m, bool dyn, cudaStream_t st);
 
 int warp_tma_backward(const float* gout, const float* src, const float* m, const float* bx, const float* by, float* gsrc, float* gm,
                       void* workspace, int B, int C, int H, int W, int h, int w, int Bm, int projective, int interp, int pad, int align,

@@ -33,7 +33,13 @@ namespace kb200 {
 // share a floor cell; stride-1 lanes are conflict-free but two neighbours fall into one cell wherever the map minifies.  The vote
 // stays warp-uniform: no duplicate in the instruction -> the un-predicated tap code; duplicates of multiplicity 2 -> two
 // predicated rounds (first-of-cell lanes, then second-of-cell lanes); deeper pile-ups -> the exact path.
-template <int NC, int PAD, bool PROJ, bool ALIGN, bool NEED_SRC, bool NEED_M, bool STRIDE1 = false>
+//
+// DYN: the work is not dealt out in advance.  The warps are independent pipelines already, so each WARP draws its next item -- one
+// 4-row slice of a chunk of tiles of a strip -- from a counter in global memory; the eight slices of a chunk are consecutive items.
+// No CTA-wide step is added.  The d/dM record of an item goes to row (chunk, slice), so the second stage sums the same partials in
+// a fixed order whatever warp produced them: still deterministic.  (Static deal, ncu at B=32: the slowest SM is active 23 % longer
+// than the average, profiles/r2_bwd_stride1_ncu_digest.txt.)
+template <int NC, int PAD, bool PROJ, bool ALIGN, bool NEED_SRC, bool NEED_M, bool STRIDE1 = false, bool DYN = false>
 __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_constant__ CUtensorMap tmap_srcwin,
                                                                 const __grid_constant__ CUtensorMap tmap_gsrc,
                                                                 const __grid_constant__ CUtensorMap tmap_gout,
@@ -58,7 +64,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
     tma::fence_barrier_init();
     if (NEED_M) tma::prefetch_map(&tmap_srcwin);
   }
-  if (NEED_M) {  // mark every record row of this CTA unused; rows are claimed as segments are processed
+  if (NEED_M && !DYN) {  // mark every record row of this CTA unused; rows are claimed as segments are processed
     for (int i = threadIdx.x; i < p.max_segs; i += blockDim.x) p.record_batch[(size_t)blockIdx.x * p.max_segs + i] = -1;
   }
   __syncthreads();  // the only CTA-wide barrier of the kernel
@@ -74,12 +80,31 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
   uint64_t* my_full = &wfull[warp];
   uint32_t phase = 0;
 
+  const int dyn_ch = DYN ? max(p.chunk_tiles, 1) : 1, dyn_cps = ceil_div(tiles_x, dyn_ch);
+  const int dyn_items = DYN ? p.B * tiles_y * dyn_cps * TMA_CONSUMER_WARPS : 0;
   int seg_strip, tx0, tx1, cursor = 0;
-  for (int seg = 0; segs.get(seg, seg_strip, tx0, tx1, cursor); ++seg) {
+  for (int seg = 0;; ++seg) {
+    int slice = warp;        // which 4-row slice of the tiles this warp takes
+    int record_row = 0;      // row of the d/dM record of this run of tiles
+    if (DYN) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(p.counter, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= dyn_items) break;
+      const int chunk = item / TMA_CONSUMER_WARPS;
+      slice = item - chunk * TMA_CONSUMER_WARPS;
+      seg_strip = chunk / dyn_cps;
+      tx0 = (chunk - seg_strip * dyn_cps) * dyn_ch;
+      tx1 = min(tiles_x, tx0 + dyn_ch);
+      record_row = chunk;
+    } else {
+      if (!segs.get(seg, seg_strip, tx0, tx1, cursor)) break;
+      record_row = blockIdx.x * p.max_segs + seg;
+    }
     const int b = seg_strip / tiles_y, ty = seg_strip - b * tiles_y;
     Mat3<float> m;
     m.load(p.m + (p.Bm == 1 ? 0 : (size_t)b * 9));
-    const int y_base = ty * TH + warp * RPW;
+    const int y_base = ty * TH + slice * RPW;
     const float* gbase = p.gout + (size_t)b * NC * oplane;
     float pm[9];  // d/dm partials of this thread over the whole segment
 #pragma unroll
@@ -122,7 +147,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
         sox = win_ok ? max(ox, 0) : 0x20000000;
         soy = win_ok ? max((int)floorf(lo_y), 0) : 0x20000000;
       }
-      if (warp == 0 && tx + 1 < tx1 && tma::elect_one()) tma::prefetch_3d(&tmap_gout, (tx + 1) * TW, ty * TH, b * NC);
+      if (slice == 0 && tx + 1 < tx1 && tma::elect_one()) tma::prefetch_3d(&tmap_gout, (tx + 1) * TW, ty * TH, b * NC);
       __syncwarp();
 
       // lane <-> output columns (2 lane, 2 lane + 1): inside one instruction the lanes are two pixels apart, so
@@ -355,11 +380,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
         pm[k] = v;
       }
       if (lane == 0) {
-        const size_t row = (size_t)blockIdx.x * p.max_segs + seg;
-        float* rec = p.records + (row * TMA_CONSUMER_WARPS + warp) * 9;
+        float* rec = p.records + ((size_t)record_row * TMA_CONSUMER_WARPS + slice) * 9;
 #pragma unroll
         for (int k = 0; k < 9; ++k) rec[k] = pm[k];
-        if (warp == 0) p.record_batch[row] = b;
+        if (slice == 0) p.record_batch[record_row] = b;
       }
     }
   }

@@ -204,6 +204,38 @@ def test_tiled_backward_matches_generic(stride1, pad, ac, C):
                 assert rel_l2(gm_only[b], gm2[b]) < 1e-5
 
 
+def test_backward_work_drawn_at_run_time_matches_the_static_deal():
+    """warp_bwd_tma2<DYN> (every warp draws its next 4-row slice of a chunk of tiles from a counter; switch dyn_sched) against the
+    static deal at a shape with enough strips for the dispatcher to take it: d/dsrc up to the order of the reduce-adds, d/dM up to
+    the grouping of the partial sums; and each gradient alone."""
+    from helpers import rel_l2
+    from test_parity_gpu import _bench_homographies
+
+    B, H, W = 400, 96, 192   # 1 200 strips of three tiles
+    g = torch.Generator().manual_seed(2)
+    src = torch.rand(B, 3, H, W, generator=g).to(DEV)
+    M = _bench_homographies(B, H, W, 11, sigma=2.0).to(DEV)
+    cot = (torch.rand(B, 3, H, W, generator=g) - 0.5).to(DEV)
+
+    def grads(want=(True, True)):
+        s, mm = src.clone().requires_grad_(want[0]), M.clone().requires_grad_(want[1])
+        out = K.warp_perspective(s, mm, (H, W))
+        return torch.autograd.grad(out, [t for t, w in zip((s, mm), want) if w], grad_outputs=cot)
+
+    with K.config.override(dyn_sched=0):
+        gs0, gm0 = grads()
+    with K.config.override(dyn_sched=1):
+        gs1, gm1 = grads()
+        (gs_only,) = grads((True, False))
+        (gm_only,) = grads((False, True))
+        gs2, gm2 = grads()
+    assert rel_l2(gs1, gs0) < 2e-6 and rel_l2(gs_only, gs0) < 2e-6
+    torch.testing.assert_close(gs1, gs0, rtol=1e-4, atol=2e-5)
+    for b in range(B):
+        assert rel_l2(gm1[b], gm0[b]) < 1e-4, (b, rel_l2(gm1[b], gm0[b]))
+    assert torch.equal(gm1, gm2) and torch.equal(gm_only, gm1)   # the record rows are summed in a fixed order: run-to-run identical
+
+
 @pytest.mark.parametrize("stride1", [0, 1])
 def test_tiled_backward_720p_and_goldens(stride1):
     """cfg4's shape at reduced batch against the reference's autograd on CPU, and every golden gradient case."""

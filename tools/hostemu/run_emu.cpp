@@ -510,7 +510,7 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
   }
   const int nstrips = B * ceil_div(h, 32), max_segs = nstrips / (int)grid + 2;
   const size_t rows = (size_t)grid * max_segs;
-  long long exact[4] = {0, 0, 0, 0};
+  long long exact[6] = {0, 0, 0, 0, 0, 0};
   auto run = [&](int version, float* gsrc, std::vector<double>& gm) {
     emu_exact_path_pixels = 0;
     for (size_t i = 0; i < ns; ++i) gsrc[i] = 0.f;
@@ -523,11 +523,22 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
     const CUtensorMap mgsrc = emu::make_map(gsrc, W, H, B * C, 72, BWD_SH, C), mgout = emu::make_map(gout, w, h, B * C, 64, 32, C);
     emu::set_smem(bwd2_smem, sizeof(bwd2_smem));
     const CUtensorMap mwin = emu::make_map(src, W, H, B * C, 72, BWD_SH, C);
+    int counter = 0;
+    size_t use_rows = rows;
+    if (version == 5) {  // the run-time work distribution: one record row per chunk, chunk = 3 tiles here
+      p.counter = &counter;
+      p.chunk_tiles = 3;
+      use_rows = (size_t)B * ceil_div(h, 32) * ceil_div(ceil_div(w, 64), 3);
+      records.assign(use_rows * 8 * 9, 0.f);
+      rb.assign(use_rows, -7);
+      p.records = records.data(); p.record_batch = rb.data();
+      emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true, true, true>(mwin, mgsrc, mgout, p); });
+    } else
     if (version == 2) emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true, false>(mwin, mgsrc, mgout, p); });
     else emu::launch(grid, dim3(BWD_THREADS), [&] { warp_bwd_tma2<C, KB200_ZEROS, PROJ, ALIGN, true, true, true>(mwin, mgsrc, mgout, p); });
     exact[version] = emu_exact_path_pixels;
     gm.assign((size_t)B * 9, 0.0);
-    for (size_t r = 0; r < rows; ++r)
+    for (size_t r = 0; r < use_rows; ++r)
       if (rb[r] >= 0)
         for (int wv = 0; wv < 8; ++wv)
           for (int k = 0; k < 9; ++k) gm[(size_t)rb[r] * 9 + k] += (double)records[(r * 8 + wv) * 9 + k];
@@ -537,8 +548,12 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
   float* g1 = aligned(g1s, ns);
   float* g2 = aligned(g2s, ns);
   std::vector<double> gm1, gm2;
+  std::vector<float> g5s;
+  float* g5 = aligned(g5s, ns);
+  std::vector<double> gm5;
   run(2, g1, gm1);
   run(3, g2, gm2);
+  run(5, g5, gm5);
   auto check = [&](const char* name, const float* g, const std::vector<double>& gm) {
     double num = 0, den = 0, worst = 0;
     for (size_t i = 0; i < ns; ++i) {
@@ -556,6 +571,7 @@ static void test_backward(int B, int H, int W, int h, int w, unsigned grid, bool
   printf("     pixels on the exact (global-memory) path: warp_bwd_tma2 %lld, stride-1 lanes %lld of %d\n", exact[2], exact[3], B * h * w);
   check("warp_bwd_tma2 (per-warp pipelines) vs fp64 scalar backward", g1, gm1);
   check("warp_bwd_tma2<STRIDE1> (conflict-free lanes) vs fp64 scalar backward", g2, gm2);
+  check("warp_bwd_tma2<STRIDE1, DYN> (work drawn at run time) vs fp64 scalar backward", g5, gm5);
 }
 
 // Random shapes, grids and completion modes (run_emu --fuzz N): shakes out the edge cases the fixed list does not name

@@ -19,7 +19,9 @@ many = torch.rand(400, 3, 96, 192, generator=g).to(dev)
 Mmany = M[:1].expand(400, -1, -1).contiguous()
 K.warp_perspective(many, Mmany, (96, 192))
 K.warp_affine(many, Mmany[:, :2].contiguous(), (96, 192), align_corners=False)
-del many
+sm, mm = many.clone().requires_grad_(True), Mmany.clone().requires_grad_(True)   # ... and of the backward kernel (warp_bwd_tma2<DYN>)
+torch.autograd.grad(K.warp_perspective(sm, mm, (96, 192)).sum(), [sm, mm])
+del many, sm, mm
 s = src.clone().requires_grad_(True)
 m = M.clone().requires_grad_(True)
 out = K.warp_perspective(s, m, (H, W))
