@@ -14,10 +14,10 @@
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
  *   - return value: 0 on success, a negative KB200_E* code otherwise; kb200_last_error()
  *     returns a thread-local message for the last failing call;
- *   - scratch is caller-provided (see *_workspace_bytes).  One exception, in stream order and invisible to the caller: with the
- *     run-time work distribution on (option "dyn_sched", the default) kb200_warp_forward / kb200_warp_backward take a 4-byte work
- *     counter per launch from the device's default memory pool (cudaMallocAsync + cudaMemsetAsync ... cudaFreeAsync on `stream`;
- *     legal inside a stream capture).  kb200_set_option("dyn_sched", 0) restores allocation-free calls.
+ *   - scratch is caller-provided (see *_workspace_bytes).  One exception: with the run-time work distribution on (option
+ *     "dyn_sched", the default, for kb200_warp_forward / kb200_warp_backward) the first such launch on a device allocates a 128 KB
+ *     ring of work counters (cudaMalloc, kept for the life of the process) and every launch zeroes one of them on `stream`
+ *     (cudaMemsetAsync: legal inside a stream capture).  With the option 0 no call allocates.
  */
 #ifndef KORNIA_B200_H
 #define KORNIA_B200_H
@@ -55,7 +55,7 @@ const char* kb200_last_warp_variant(void);
  * samples, 32x32 tiles for rotated / sheared ones; each kernel skips the other's samples). */
 int kb200_last_warp_launches(void);
 /* Kernel-selection switches: which of the library's own kernels serves a request.  Names: "tma", "tiled_filter",
- * "square_tiles", "sep_vwalk", "tiled_gradient", "u8_tiled", "bwd_stride1", "remap_piped" (2 = also under 'reflection'), "dyn_sched"; values 0 = off, 1 = on, -1 = the
+ * "square_tiles", "sep_vwalk", "tiled_gradient", "u8_tiled", "bwd_stride1", "remap_piped" (2 = also under 'reflection'), "dyn_sched", "dyn_chunk" (tiles), "dyn_static" (percent); values 0 = off, 1 = on, -1 = the
  * dispatcher's own rule.
  * Each is initialised ONCE when the library is loaded (environment KB200_<NAME>, else the built-in default); there is no
  * getenv on the call path.  The parity tests use the setter to run a tiled kernel against the kernel it stands in for.

@@ -11,8 +11,9 @@ kernels), ``tiled_filter`` (shared-memory filter kernels; off = generic), ``squa
 rotated samples), ``sep_vwalk`` (band-walking separable filter: -1 auto = 11 taps and more, 0 never, 1 whenever it
 applies), ``tiled_gradient``, ``u8_tiled`` (staged-window uint8 ingest warp; off = per-tap kernel), ``bwd_stride1`` (tiled
 backward on stride-1 lanes; off = column-pair lanes), ``remap_piped`` (pipelined persistent remap kernel for 'zeros' / 'border';
-off = one CTA per tile; 2 = also under 'reflection', for measurements), ``dyn_sched`` (headline warp: strips handed out at run
-time in chunks; off = dealt out in advance).
+off = one CTA per tile; 2 = also under 'reflection', for measurements), ``dyn_sched`` (warp forward and backward: the last rounds of
+strips / every warp's work drawn at run time from a per-device ring of counters; off = dealt out in advance), ``dyn_chunk`` (tiles
+per chunk, 10), ``dyn_static`` (percent of the full rounds the forward kernel still deals out in advance, 85).
 Host-side: ``fused_pyrdown`` (5x5 blur + 2x decimation in one kernel), ``fused_undistort`` (lens model evaluated inside
 the sampling kernel), ``fast_filter_bwd`` (input gradient of the separable filter through the one-pass forward kernel),
 ``torch_prelude`` (the (B,3,3) matrix chain as the reference's torch op sequence instead of one launch; needed for double
@@ -25,7 +26,7 @@ import os
 
 from . import _lib
 
-DEVICE_OPTIONS = ("tma", "tiled_filter", "square_tiles", "sep_vwalk", "tiled_gradient", "u8_tiled", "bwd_stride1", "remap_piped", "dyn_sched")
+DEVICE_OPTIONS = ("tma", "tiled_filter", "square_tiles", "sep_vwalk", "tiled_gradient", "u8_tiled", "bwd_stride1", "remap_piped", "dyn_sched", "dyn_chunk", "dyn_static")
 _HOST_DEFAULTS = {"fused_pyrdown": 1, "fused_undistort": 1, "fast_filter_bwd": 1, "torch_prelude": 0}
 
 

@@ -28,8 +28,8 @@ void set_error(const char* fmt, ...) {
 }
 
 // ---------------------------------------------------------------- kernel-selection switches (common.cuh: enum Option)
-static const char* const OPTION_NAMES[OPT_COUNT] = {"tma", "tiled_filter", "square_tiles", "sep_vwalk", "tiled_gradient", "u8_tiled", "bwd_stride1", "remap_piped", "dyn_sched"};
-static const int OPTION_DEFAULTS[OPT_COUNT] = {1, 1, 1, -1, 1, 1, 1, 1, 1};
+static const char* const OPTION_NAMES[OPT_COUNT] = {"tma", "tiled_filter", "square_tiles", "sep_vwalk", "tiled_gradient", "u8_tiled", "bwd_stride1", "remap_piped", "dyn_sched", "dyn_chunk", "dyn_static"};
+static const int OPTION_DEFAULTS[OPT_COUNT] = {1, 1, 1, -1, 1, 1, 1, 1, 1, 10, 85};
 static int g_options[OPT_COUNT];
 static const bool g_options_ready = [] {  // once, when the library is loaded: KB200_<NAME>=<int> overrides the default
   for (int i = 0; i < OPT_COUNT; ++i) {

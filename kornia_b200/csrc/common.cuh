@@ -87,6 +87,8 @@ enum Option {
   OPT_BWD_STRIDE1,     // tiled backward on stride-1 lanes (default; 0: the column-pair lanes, 5 % slower at cfg4)
   OPT_REMAP_PIPED,     // remap on the pipelined persistent kernel (off: one CTA per tile)
   OPT_DYN_SCHED,       // headline warp: strips handed out at run time in chunks (off: dealt out in advance)
+  OPT_DYN_CHUNK,       // tiles per chunk of the run-time work distribution (forward kernel)
+  OPT_DYN_STATIC,      // percent of the full rounds of strips still dealt out in advance by the DYN forward kernel
   OPT_COUNT
 };
 int option(Option o);
@@ -100,6 +102,43 @@ inline bool needs_attribute_on_device(const unsigned long long& mask, int& dev) 
   return (__atomic_load_n(&mask, __ATOMIC_ACQUIRE) & (1ull << (dev & 63))) == 0;
 }
 inline void attribute_applied_on_device(unsigned long long& mask, int dev) { __atomic_fetch_or(&mask, 1ull << (dev & 63), __ATOMIC_RELEASE); }
+
+// Work counters of the run-time work distribution: a ring of 1 024 counters per device, allocated once (128 KB, the library's only
+// device allocation), one slot per launch, zeroed on the launch's stream.  A slot comes round again after 1 024 launches; two
+// launches could only share one if the first were still running then.  (The first version took each counter from the default
+// memory pool with cudaMallocAsync / cudaFreeAsync around the launch: whole runs of the headline bench then landed at 0.85 of the
+// roofline among runs at 0.93, profiles/r2_ab_headline_dyn.txt.)
+inline int* take_work_counter(cudaStream_t st) {
+  constexpr int SLOTS = 1024, STRIDE = 32;  // ints: one counter per 128-byte line
+  static int* base[64] = {nullptr};
+  static unsigned long long seq[64] = {0};
+  static int lock = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  int* b = __atomic_load_n(&base[dev], __ATOMIC_ACQUIRE);
+  if (!b) {
+    while (__atomic_exchange_n(&lock, 1, __ATOMIC_ACQUIRE)) {
+    }
+    b = base[dev];
+    if (!b) {
+      void* ptr = nullptr;
+      if (cudaMalloc(&ptr, (size_t)SLOTS * STRIDE * sizeof(int)) == cudaSuccess) {
+        b = static_cast<int*>(ptr);
+        __atomic_store_n(&base[dev], b, __ATOMIC_RELEASE);
+      } else {
+        (void)cudaGetLastError();
+      }
+    }
+    __atomic_store_n(&lock, 0, __ATOMIC_RELEASE);
+    if (!b) return nullptr;
+  }
+  int* slot = b + (size_t)(__atomic_fetch_add(&seq[dev], 1ull, __ATOMIC_RELAXED) % SLOTS) * STRIDE;
+  if (cudaMemsetAsync(slot, 0, sizeof(int), st) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return slot;
+}
 
 #define KB_SET_SMEM_ONCE(mask, kern, bytes)                                                                   \
   do {                                                                                                       \

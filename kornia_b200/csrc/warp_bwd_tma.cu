@@ -56,16 +56,12 @@ int warp_tma_backward(const float* gout, const float* src, const float* m, const
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return KB200_EUNSUPPORTED;
   }
-  if (dyn) {  // the launch's own work counter, allocated and released in stream order
-    if (cudaMallocAsync(reinterpret_cast<void**>(&p.counter), sizeof(int), st) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return KB200_EUNSUPPORTED;
-    }
-    cudaMemsetAsync(p.counter, 0, sizeof(int), st);
+  if (dyn) {
+    p.counter = take_work_counter(st);
+    if (!p.counter) return KB200_EUNSUPPORTED;
     p.chunk_tiles = BWD_DYN_CHUNK;
   }
   const int rc = launch_warp_bwd_tma2(msrcwin, mgsrc, mgout, p, C, pad, projective, align, gsrc != nullptr, gm != nullptr, dyn, st);
-  if (dyn) cudaFreeAsync(p.counter, st);
   if (rc != KB200_OK || !gm) return rc;
   warp_gm_reduce_records<<<dim3(9, Bm), 256, 0, st>>>(p.records, p.record_batch, gm, (int)rows, Bm,
                                                         dyn ? (int)(rows / (size_t)B) : 0);

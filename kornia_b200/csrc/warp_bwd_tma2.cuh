@@ -83,14 +83,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) warp_bwd_tma2(const __grid_con
   const int dyn_ch = DYN ? max(p.chunk_tiles, 1) : 1, dyn_cps = ceil_div(tiles_x, dyn_ch);
   const int dyn_items = DYN ? p.B * tiles_y * dyn_cps * TMA_CONSUMER_WARPS : 0;
   int seg_strip, tx0, tx1, cursor = 0;
+  int drawn = 0;  // DYN: the item this warp drew ahead
+  if (DYN && lane == 0) drawn = atomicAdd(p.counter, 1);
   for (int seg = 0;; ++seg) {
     int slice = warp;        // which 4-row slice of the tiles this warp takes
     int record_row = 0;      // row of the d/dM record of this run of tiles
     if (DYN) {
-      int item = 0;
-      if (lane == 0) item = atomicAdd(p.counter, 1);
-      item = __shfl_sync(0xffffffffu, item, 0);
+      const int item = __shfl_sync(0xffffffffu, drawn, 0);
       if (item >= dyn_items) break;
+      if (lane == 0) drawn = atomicAdd(p.counter, 1);  // the next item: its round trip through L2 overlaps this one's tiles
       const int chunk = item / TMA_CONSUMER_WARPS;
       slice = item - chunk * TMA_CONSUMER_WARPS;
       seg_strip = chunk / dyn_cps;

@@ -18,17 +18,14 @@ static int launch_warp_tma(const CUtensorMap& map, const TmaWarpParams& p, cudaS
   const long long nstrips = (long long)p.B * ceil_div(p.h, TH);
   const long long cap = (long long)ctas_per_sm * sm_count();
   const int grid = (int)(nstrips < cap ? nstrips : cap);
-  if (DYN) {  // a work counter of this launch's own, allocated and released in stream order (graph-capturable, no sharing between launches)
+  if (DYN) {
     TmaWarpParams q = p;
-    if (cudaMallocAsync(reinterpret_cast<void**>(&q.counter), sizeof(int), st) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return KB200_EUNSUPPORTED;
-    }
-    cudaMemsetAsync(q.counter, 0, sizeof(int), st);
-    q.chunk_tiles = 10;
+    q.counter = take_work_counter(st);
+    if (!q.counter) return KB200_EUNSUPPORTED;
+    q.chunk_tiles = option(OPT_DYN_CHUNK) > 0 ? option(OPT_DYN_CHUNK) : 10;
+    q.static_pct = option(OPT_DYN_STATIC);
     kern<<<grid, TMA_THREADS, smem, st>>>(map, q);
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(q.counter, st);
     if (e != cudaSuccess) {
       set_error("warp_fwd_tma<DYN> launch failed: %s", cudaGetErrorString(e));
       return KB200_ECUDA;
@@ -68,7 +65,7 @@ static int warp_tma_forward_impl(const TmaFwdArgs& a, cudaStream_t st) {
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return KB200_EUNSUPPORTED;
-  TmaWarpParams p{a.src, a.m, a.bx, a.by, a.fill, a.out, a.B, a.H, a.W, a.h, a.w, a.Bm, a.align, a.only_class, nullptr, 0};
+  TmaWarpParams p{a.src, a.m, a.bx, a.by, a.fill, a.out, a.B, a.H, a.W, a.h, a.w, a.Bm, a.align, a.only_class, nullptr, 0, 0};
   const int C = a.C, pad = a.pad;
   const bool projective = a.projective != 0, align = a.align != 0;
   // run-time work distribution (warp_fwd_tma<DYN>) for bilinear RGB batches with enough strips to go round several times

@@ -32,7 +32,7 @@ int warp_tma_forward_square(const TmaFwdArgs& a, cudaStream_t st) {
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return KB200_EUNSUPPORTED;
-  const TmaWarpParams p{a.src, a.m, a.bx, a.by, a.fill, a.out, a.B, a.H, a.W, a.h, a.w, a.Bm, a.align, a.only_class, nullptr, 0};
+  const TmaWarpParams p{a.src, a.m, a.bx, a.by, a.fill, a.out, a.B, a.H, a.W, a.h, a.w, a.Bm, a.align, a.only_class, nullptr, 0, 0};
   const bool projective = a.projective != 0, align = a.align != 0;
 #define KB_SQ_CASE(NC_, PAD_) \
   if (a.C == NC_ && a.pad == PAD_) return launch_square<NC_, PAD_>(map, p, projective, align, st);

@@ -435,7 +435,7 @@ static void test_forward(int B, int H, int W, int h, int w, unsigned grid, bool 
       for (size_t i = 0; i < no; ++i) o3[i] = -5.f;
       int counter = 0;
       TmaWarpParams q = p;
-      q.out = o3; q.counter = &counter; q.chunk_tiles = chunk;
+      q.out = o3; q.counter = &counter; q.chunk_tiles = chunk; q.static_pct = chunk == 3 ? 50 : (chunk == 10 ? 100 : 0);
       emu::launch(grid, dim3(TMA_THREADS), [&] { warp_fwd_tma<C, INTERP, PAD, PROJ, ALIGN, TW, TH, BW, BH, 2, true>(map, q); });
       p.out = o3;  // keep the comparison below on o1
       p.out = o1;
