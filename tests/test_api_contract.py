@@ -168,6 +168,31 @@ def test_c_abi_exports_every_declared_symbol():
     assert sorted(_lib.SIGNATURES) == names, "python binding and header disagree"
 
 
+def test_kernel_selection_switches_agree_everywhere():
+    """The option table of the C library, kornia_b200.config and the header's list name the same switches; unknown names are
+    refused; a set is read back.  (No GPU needed: the table lives on the host.)"""
+    import re
+    from kornia_b200 import config
+
+    lib = _lib.load()
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "kornia_b200.h")).read()
+    block = header[header.index("Kernel-selection switches"):header.index("int kb200_set_option")]
+    named = set(re.findall(r'"([a-z0-9_]+)"', block))
+    assert named == set(config.DEVICE_OPTIONS), (sorted(named), sorted(config.DEVICE_OPTIONS))
+    int_min = -(2 ** 31)
+    for name in config.DEVICE_OPTIONS:
+        before = lib.kb200_get_option(name.encode())
+        assert before != int_min, name
+        assert lib.kb200_set_option(name.encode(), before) == 0
+        assert lib.kb200_get_option(name.encode()) == before
+    assert lib.kb200_get_option(b"no_such_switch") == int_min
+    assert lib.kb200_set_option(b"no_such_switch", 1) != 0
+    config.set("dyn_chunk", 7)
+    assert config.get("dyn_chunk") == 7 and lib.kb200_get_option(b"dyn_chunk") == 7
+    config.reset()
+    assert config.get("dyn_chunk") == 10 and config.get("dyn_sched") == 1 and config.get("dyn_static") == 85
+
+
 def test_c_abi_version_and_error_channel():
     lib = _lib.load()
     assert lib.kb200_abi_version() == _lib.ABI_VERSION
